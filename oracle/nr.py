@@ -1,0 +1,276 @@
+"""Oracle restatement of the Newton-Raphson AC power flow (TEST INFRASTRUCTURE).
+
+Reference lines followed (all under /root/reference/src):
+  initializeACPowerFlow / changeSlackBus!   powerFlow/acPowerFlow.jl:1312-1358
+  newtonJacobian                           powerFlow/acPowerFlow.jl:89-175
+  mismatch!                                powerFlow/acPowerFlow.jl:645-685  (+ backend/equations.jl:63-103,126)
+  solve! (Jacobian fill, update)           powerFlow/acPowerFlow.jl:793-911  (+ backend/equations.jl:105-143)
+  powerFlow! loop                          powerFlow/acPowerFlow.jl:1389-1433
+  factorization/solution!                  backend/utility.jl:470-586 -> SuiteSparse (third party); here SuperLU.
+
+The scalar loops are written exactly in the reference's order so summation order (and therefore the
+last bits of every value) matches the reference's arithmetic.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from math import sin, cos
+import numpy as np
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+from .system import System
+from .model import AcModel, ac_model
+
+
+@dataclass
+class NewtonRaphson:
+    sys: System
+    mdl: AcModel
+    bus_type: np.ndarray     # after the PV->PQ / slack fix-ups of initializeACPowerFlow
+    slack: int
+    vm: np.ndarray           # analysis.voltage.magnitude
+    va: np.ndarray           # analysis.voltage.angle
+    pq: np.ndarray           # 0-based position in the mismatch vector, -1 if not PQ
+    pvpq: np.ndarray         # 0-based, -1 for the slack bus
+    pcount: np.ndarray
+    j_colptr: np.ndarray     # 0-based CSC pattern of the Jacobian
+    j_rowval: np.ndarray
+    j_nzval: np.ndarray
+    mismatch: np.ndarray
+    increment: np.ndarray
+    iteration: int = 0
+    lu_options: dict | None = None
+
+    @property
+    def dim(self) -> int:
+        return len(self.mismatch)
+
+
+def initialize(sys: System):
+    """initializeACPowerFlow + changeSlackBus! (acPowerFlow.jl:1312-1358). Returns copies; `sys` untouched."""
+    bus_type = sys.bus_type.copy()
+    slack = sys.slack
+    vm = sys.vm.copy()
+    va = sys.va.copy()
+    for i in range(sys.n):
+        has_gen = len(sys.bus_gens[i]) > 0
+        if not has_gen and bus_type[i] == 2:
+            bus_type[i] = 1
+        if has_gen and bus_type[i] != 1:
+            vm[i] = sys.gen_vm[sys.bus_gens[i][0]]
+    if len(sys.bus_gens[slack]) == 0:
+        bus_type[slack] = 1
+        for i in range(sys.n):
+            if bus_type[i] == 2 and len(sys.bus_gens[i]) > 0:
+                bus_type[i] = 3
+                slack = i
+                break
+        if bus_type[slack] == 1:
+            raise RuntimeError("The slack bus is missing.")
+    return bus_type, slack, vm, va
+
+
+def newton_jacobian(mdl: AcModel, bus_type: np.ndarray, slack: int):
+    """Index maps and CSC pattern of the Jacobian (acPowerFlow.jl:89-175), 0-based."""
+    n = mdl.n
+    pq = np.full(n, -1, dtype=np.int64)
+    pvpq = np.full(n, -1, dtype=np.int64)
+    pvpq_num = 0
+    pq_num = 0
+    for i in range(n):
+        if bus_type[i] == 1:
+            pq[i] = pq_num + n - 1
+            pq_num += 1
+        if bus_type[i] != 3:
+            pvpq[i] = pvpq_num
+            pvpq_num += 1
+    dim = n + pq_num - 1
+    colcount = np.zeros(dim, dtype=np.int64)
+    pcount = np.zeros(n, dtype=np.int64)
+    qcount = np.zeros(n, dtype=np.int64)
+    for i in range(n):
+        if i == slack:
+            continue
+        for ptr in range(mdl.colptr[i], mdl.colptr[i + 1]):
+            t = bus_type[mdl.rowval[ptr]]
+            if t != 3:
+                pcount[i] += 1
+            if t == 1:
+                qcount[i] += 1
+        colcount[pvpq[i]] = pcount[i] + qcount[i]
+        if bus_type[i] == 1:
+            colcount[pq[i]] = pcount[i] + qcount[i]
+    colptr = np.zeros(dim + 1, dtype=np.int64)
+    colptr[1:] = np.cumsum(colcount)
+    nnz = int(colptr[-1])
+    rowval = np.zeros(nnz, dtype=np.int64)
+    for i in range(n):
+        if i == slack:
+            continue
+        is_pq = bus_type[i] == 1
+        pa = colptr[pvpq[i]]
+        qa = pa + pcount[i]
+        pm = colptr[pq[i]] if is_pq else 0
+        qm = pm + pcount[i] if is_pq else 0
+        for ptr in range(mdl.colptr[i], mdl.colptr[i + 1]):
+            row = mdl.rowval[ptr]
+            t = bus_type[row]
+            if t != 3:
+                rowval[pa] = pvpq[row]
+                pa += 1
+                if is_pq:
+                    rowval[pm] = pvpq[row]
+                    pm += 1
+            if t == 1:
+                rowval[qa] = pq[row]
+                qa += 1
+                if is_pq:
+                    rowval[qm] = pq[row]
+                    qm += 1
+    return pq, pvpq, pcount, colptr, rowval
+
+
+def newton_raphson(sys: System, mdl: AcModel | None = None, lu_options: dict | None = None) -> NewtonRaphson:
+    """newtonRaphson(system) (acPowerFlow.jl:39-87)."""
+    if mdl is None:
+        mdl = ac_model(sys)
+    bus_type, slack, vm, va = initialize(sys)
+    pq, pvpq, pcount, colptr, rowval = newton_jacobian(mdl, bus_type, slack)
+    dim = len(colptr) - 1
+    return NewtonRaphson(sys, mdl, bus_type, slack, vm, va, pq, pvpq, pcount, colptr, rowval,
+                         np.zeros(len(rowval)), np.zeros(dim), np.zeros(dim), 0, lu_options)
+
+
+def mismatch(a: NewtonRaphson):
+    """mismatch!(analysis) (acPowerFlow.jl:645-685). Returns (stopP, stopQ)."""
+    m, sys = a.mdl, a.sys
+    V, T = a.vm, a.va
+    stop_p = 0.0
+    stop_q = 0.0
+    for i in range(m.n):
+        if i == a.slack:
+            continue
+        k = a.pvpq[i]
+        q = a.pq[i]
+        cur_p = 0.0
+        cur_q = 0.0
+        is_pq = a.bus_type[i] == 1
+        for ptr in range(m.colptr[i], m.colptr[i + 1]):
+            row = m.rowval[ptr]
+            y = m.nzval_t[ptr]                      # Y[i,row] (equations.jl:63-68)
+            G, B = y.real, y.imag
+            d = T[i] - T[row]
+            s, c = sin(d), cos(d)
+            cur_p += V[row] * (G * c + B * s)       # PiQiSumPlus (equations.jl:78-87)
+            if is_pq:
+                cur_q += V[row] * (G * s - B * c)   # PiQiSumMinus (equations.jl:89-98)
+        a.mismatch[k] = V[i] * cur_p - sys.supply_p[i] + sys.pd[i]
+        stop_p = max(stop_p, abs(a.mismatch[k]))
+        if is_pq:
+            a.mismatch[q] = V[i] * cur_q - sys.supply_q[i] + sys.qd[i]
+            stop_q = max(stop_q, abs(a.mismatch[q]))
+    return stop_p, stop_q
+
+
+def fill_jacobian(a: NewtonRaphson):
+    """Jacobian fill of solve! (acPowerFlow.jl:813-888)."""
+    m = a.mdl
+    V, T = a.vm, a.va
+    nz = a.j_nzval
+    for i in range(m.n):
+        if i == a.slack:
+            continue
+        is_pq = a.bus_type[i] == 1
+        pa = a.j_colptr[a.pvpq[i]]
+        qa = pa + a.pcount[i]
+        pm = a.j_colptr[a.pq[i]] if is_pq else 0
+        qm = pm + a.pcount[i] if is_pq else 0
+        for j in range(m.colptr[i], m.colptr[i + 1]):
+            row = m.rowval[j]
+            t = a.bus_type[row]
+            if t == 3:
+                continue
+            y = m.nzval[j]                          # Y[row,i]
+            G, B = y.real, y.imag
+            if row != i:
+                d = T[row] - T[i]
+                s, c = sin(d), cos(d)
+                nz[pa] = V[row] * V[i] * (G * s - B * c)            # Piθj (equations.jl:109)
+                pa += 1
+                if t == 1:
+                    nz[qa] = -V[row] * V[i] * (G * c + B * s)       # Qiθj (:134)
+                    qa += 1
+                if is_pq:
+                    nz[pm] = V[row] * (G * c + B * s)               # PiVj (:117)
+                    pm += 1
+                if is_pq and t == 1:
+                    nz[qm] = V[row] * (G * s - B * c)               # QiVj (:142)
+                    qm += 1
+            else:
+                cur_t = 0.0
+                cur_v = 0.0
+                for ptr in range(m.colptr[i], m.colptr[i + 1]):
+                    q = m.rowval[ptr]
+                    yk = m.nzval_t[ptr]
+                    Gk, Bk = yk.real, yk.imag
+                    d = T[i] - T[q]
+                    s, c = sin(d), cos(d)
+                    cur_t += V[q] * (Gk * s - Bk * c)               # PiQiSumMinus
+                    if is_pq:
+                        cur_v += V[q] * (Gk * c + Bk * s)           # PiQiSumPlus
+                nz[pa] = V[row] * (-cur_t) - B * V[row] ** 2        # Piθi (:105)
+                pa += 1
+                if is_pq:
+                    nz[qa] = V[row] * cur_v - G * V[row] ** 2       # Qiθi (:130)
+                    qa += 1
+                    nz[pm] = cur_v + G * V[row]                     # PiVi (:113)
+                    pm += 1
+                    nz[qm] = cur_t - B * V[row]                     # QiVi (:138)
+                    qm += 1
+
+
+def jacobian_csc(a: NewtonRaphson) -> sp.csc_matrix:
+    return sp.csc_matrix((a.j_nzval, a.j_rowval, a.j_colptr), shape=(a.dim, a.dim))
+
+
+def solve(a: NewtonRaphson):
+    """solve!(analysis) (acPowerFlow.jl:793-911): fill J, factor, solve, update state."""
+    fill_jacobian(a)
+    opts = a.lu_options or {}
+    lu = spla.splu(jacobian_csc(a), **opts)         # stands in for UMFPACK/KLU (utility.jl:470-500)
+    a.increment[:] = lu.solve(a.mismatch)           # solution! (utility.jl:576-582)
+    for i in range(a.mdl.n):
+        if a.bus_type[i] == 1:
+            a.vm[i] = a.vm[i] - a.increment[a.pq[i]]
+        if i != a.slack:
+            a.va[i] = a.va[i] - a.increment[a.pvpq[i]]
+    a.iteration += 1
+
+
+def power_flow(a: NewtonRaphson, iteration: int = 20, tolerance: float = 1e-8, trace: list | None = None):
+    """powerFlow!(analysis) loop (acPowerFlow.jl:1389-1433). Returns converged flag."""
+    a.iteration = 0
+    converged = False
+    for _ in range(iteration + 1):
+        dp, dq = mismatch(a)
+        if trace is not None:
+            trace.append((dp, dq))
+        if dp < tolerance and dq < tolerance:
+            converged = True
+            break
+        if a.iteration == iteration:
+            break
+        solve(a)
+    return converged
+
+
+def export_one_based(a: NewtonRaphson) -> dict:
+    """The reference's own 1-based Int64 arrays (pq/pvpq use 0 for 'absent')."""
+    return {
+        "pq": (a.pq + 1).astype(np.int64),
+        "pvpq": (a.pvpq + 1).astype(np.int64),
+        "pcount": a.pcount.astype(np.int64),
+        "j_colptr": (a.j_colptr + 1).astype(np.int64),
+        "j_rowval": (a.j_rowval + 1).astype(np.int64),
+    }
