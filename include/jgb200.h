@@ -1,0 +1,97 @@
+/* jgb200 — C ABI of the B200-native Newton-Raphson / Gauss-Newton hot path behind JuliaGrid's operator surface.
+ *
+ * The reference (mcosovic/JuliaGrid.jl v0.6.2) has no FFI of its own; its seam is Julia dispatch on the
+ * factorisation tag (`newtonRaphson(system, ::Type{T})` src/powerFlow/acPowerFlow.jl:39,
+ * `gaussNewton(monitoring, ::Type{T})` src/stateEstimation/acStateEstimation.jl:43 and the triad
+ * `factorization / factorization! / solution!` src/backend/utility.jl:470-586).  Each entry point below names
+ * the reference function it stands in for; INTEGRATION.md shows the `ccall` bindings a maintainer adds.
+ *
+ * Conventions
+ *  - Arrays are the reference's own: Float64, Int64 **1-based** indices, Int8 flags, ComplexF64 passed as
+ *    interleaved (re, im) doubles.  The library copies during the call and never keeps a host pointer.
+ *  - Every function returns an int32 status: 0 ok; 1 not converged within the iteration cap (soft, like the
+ *    reference — not an error); < 0 error: -1 bad argument, -2 CUDA error, -3 singular / non-finite pivot,
+ *    -4 pattern mismatch, -5 no CUDA device.  `jgb_last_error(ctx)` returns the message of the last error.
+ *  - A context is bound to one GPU and one stream; calls on one context must not overlap.
+ *  - There is no CPU fallback: without a CUDA device `jgb_create` fails with -5.
+ */
+#ifndef JGB200_H
+#define JGB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct jgb_ctx jgb_ctx;
+
+/* ---- context ---------------------------------------------------------------------------------------------- */
+/* `stream` is a cudaStream_t (may be NULL for a private non-blocking stream).  *rc receives the status. */
+jgb_ctx* jgb_create(int32_t device, void* stream, int32_t* rc);
+void jgb_destroy(jgb_ctx* ctx);
+const char* jgb_last_error(const jgb_ctx* ctx);          /* ctx may be NULL: error of the last failed jgb_create */
+int32_t jgb_abi_version(void);
+int32_t jgb_synchronize(jgb_ctx* ctx);
+
+/* ---- Newton-Raphson AC power flow -------------------------------------------------------------------------- */
+/* newtonRaphson(system) + newtonJacobian (acPowerFlow.jl:39-175): takes Ybus and its transpose exactly as stored
+ * in system.model.ac (nodalMatrix / nodalMatrixTranspose, same pattern), bus.layout.type, bus.layout.slack.
+ * Builds pq / pvpq / pcount, the Jacobian CSC pattern, the symbolic factorisation, and uploads everything. */
+int32_t jgb_nr_setup(jgb_ctx* ctx, int64_t n, const int64_t* y_colptr, const int64_t* y_rowval,
+                     const double* y_nzval_re_im, const double* yt_nzval_re_im, const int8_t* bus_type,
+                     int64_t slack);
+/* sizes of the Jacobian built by jgb_nr_setup */
+int32_t jgb_nr_dims(jgb_ctx* ctx, int64_t* dim_j, int64_t* nnz_j);
+/* the reference's own index arrays for bit-exact parity: NewtonRaphson.pq/pvpq/pcount, jacobian.colptr/rowval */
+int32_t jgb_nr_pattern(jgb_ctx* ctx, int64_t* pq, int64_t* pvpq, int64_t* pcount, int64_t* j_colptr,
+                       int64_t* j_rowval);
+/* bus.supply.active/reactive, bus.demand.active/reactive (read by mismatch!, acPowerFlow.jl:676-680) */
+int32_t jgb_nr_set_injection(jgb_ctx* ctx, const double* p_supply, const double* q_supply, const double* p_demand,
+                             const double* q_demand);
+/* analysis.voltage.magnitude / angle */
+int32_t jgb_nr_set_state(jgb_ctx* ctx, const double* vm, const double* va);
+int32_t jgb_nr_get_state(jgb_ctx* ctx, double* vm, double* va);
+/* value-only Ybus update on the fixed pattern (acNodalUpdate!, powerSystem/model.jl:81-110):
+ * k stored positions (1-based into nzval) with their new Y and Y-transpose values */
+int32_t jgb_nr_update_y(jgb_ctx* ctx, int64_t k, const int64_t* nz_pos, const double* y_re_im,
+                        const double* yt_re_im);
+/* mismatch!(analysis) (acPowerFlow.jl:645-685) -> (max|dP|, max|dQ|) */
+int32_t jgb_nr_mismatch(jgb_ctx* ctx, double* stop_p, double* stop_q);
+/* solve!(analysis) (acPowerFlow.jl:793-911): Jacobian fill, numeric refactor, solve, state update, iteration += 1 */
+int32_t jgb_nr_solve(jgb_ctx* ctx);
+/* method.mismatch, method.increment, method.jacobian.nzval, method.iteration (any pointer may be NULL) */
+int32_t jgb_nr_get_vectors(jgb_ctx* ctx, double* mismatch, double* increment, double* j_nzval, int64_t* iteration);
+/* powerFlow!(analysis; iteration, tolerance) loop (acPowerFlow.jl:1389-1433), convergence test on the device.
+ * Returns 0 converged / 1 iteration cap reached. */
+int32_t jgb_nr_run(jgb_ctx* ctx, int64_t max_iter, double tol, int64_t* iterations, double* stop_p, double* stop_q);
+/* S independent power flows sharing topology and symbolic factorisation (N-1 sweep: updateBranch!(status = 0),
+ * powerSystem/branch.jl:313-431, each followed by powerFlow!).  Scenario s removes branch with end buses
+ * out_from[s], out_to[s] (1-based bus indices, 0 = base case) whose Y-parameters nodalFromFrom / nodalFromTo /
+ * nodalToFrom / nodalToTo are given in dy_re_im[s][0..7].  Every scenario starts from the state last set with
+ * jgb_nr_set_state (setInitialPoint! semantics).  Outputs are S x n row-major (one row per scenario); status[s] is
+ * 0 converged, 1 iteration cap, -3 singular (islanding outage).  *total_iterations = sum of solve! calls. */
+int32_t jgb_nr_batch(jgb_ctx* ctx, int64_t S, const int64_t* out_from, const int64_t* out_to, const double* dy_re_im,
+                     int64_t max_iter, double tol, double* vm_out, double* va_out, int32_t* iterations,
+                     int8_t* status, int64_t* total_iterations);
+/* Same, but inputs already resident: out_from/out_to (int64), dy (double) and the outputs vm_out/va_out (double,
+ * S x n), iterations (int32), status (int8) are DEVICE pointers on the context's GPU. */
+int32_t jgb_nr_batch_dev(jgb_ctx* ctx, int64_t S, const int64_t* out_from_dev, const int64_t* out_to_dev,
+                         const double* dy_dev, int64_t max_iter, double tol, double* vm_out_dev, double* va_out_dev,
+                         int32_t* iterations_dev, int8_t* status_dev, int64_t* total_iterations);
+
+/* ---- statistics for roofline reports ------------------------------------------------------------------------ */
+/* key: "nr.nnz_lu", "nr.fronts", "nr.levels", "nr.flops", "nr.max_front", "nr.launches_per_iteration",
+ *      "nr.assemble_bytes" (per scenario-iteration), "nr.solve_bytes", "wls.*" likewise; kernel launch counter
+ *      "launches" (since context creation).  Unknown key -> -1. */
+double jgb_stat(jgb_ctx* ctx, const char* key);
+
+/* ---- symbolic self-check (host only, no GPU work): runs the analysis on a CSC pattern and a host replay of the
+ *      multifrontal schedule; used by the CPU test-suite to validate the maps the kernels consume. */
+int32_t jgb_selfcheck_symbolic(int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                               const int64_t* group, const double* rhs, double* x, double* stats8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* JGB200_H */

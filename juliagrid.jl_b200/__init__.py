@@ -1,0 +1,9 @@
+"""jgb200 — B200-native Newton-Raphson power flow and Gauss-Newton WLS state estimation behind JuliaGrid's
+operator surface. Host mirror in Python (Julia is not available in this image; `julia/JuliaGridB200.jl` is the
+ccall shim a JuliaGrid user loads), numerics in hand-written sm_100a CUDA behind the C ABI of include/jgb200.h.
+"""
+from ._lib import Context, JgbError, load, LIB_PATH, exported_symbols  # noqa: F401
+from .cases import PowerSystem, power_system, synthetic_grid  # noqa: F401
+from .model import AcModel, ac_model  # noqa: F401
+from .ac_power_flow import (AcPowerFlow, newton_raphson, mismatch, solve, power_flow, set_initial_point,  # noqa: F401
+                            set_voltage, update_branch, newtonRaphson, powerFlow, setInitialPoint, updateBranch)

@@ -1,0 +1,230 @@
+"""Host mirror of the reference's Newton-Raphson operator surface, backed by libjgb200.so.
+
+    newton_raphson(system)        <-> newtonRaphson(system, B200)      src/powerFlow/acPowerFlow.jl:39-87
+    mismatch(analysis)            <-> mismatch!(analysis)              :645-685
+    solve(analysis)               <-> solve!(analysis)                 :793-911
+    power_flow(analysis; ...)     <-> powerFlow!(analysis; ...)        :1389-1433
+    set_initial_point(analysis)   <-> setInitialPoint!(analysis)       :1226-1249
+    update_branch(analysis, k, status) <-> updateBranch!(analysis; label, status)  powerSystem/branch.jl:453-475
+
+Argument meaning and error behaviour follow the reference: non-convergence is not an error (the last iterate stays in
+`analysis.voltage`), a singular Jacobian raises. All numerics run in CUDA; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from . import _lib
+from ._lib import Context, ptr, f64, i64, i8, cplx
+from .cases import PowerSystem
+from .model import AcModel, ac_model
+
+
+@dataclass
+class Polar:
+    magnitude: np.ndarray
+    angle: np.ndarray
+
+
+class NewtonRaphsonMethod:
+    """analysis.method — host mirrors of NewtonRaphson{T} (src/definition/analysis.jl:154-164)."""
+
+    def __init__(self):
+        self.pq = self.pvpq = self.pcount = None           # 1-based Int64 like the reference
+        self.jacobian_colptr = self.jacobian_rowval = None
+        self.iteration = 0
+        self.dim = 0
+
+
+class AcPowerFlow:
+    def __init__(self, system: PowerSystem, ctx: Context):
+        self.system = system
+        self.ctx = ctx
+        self.voltage: Polar = None
+        self.method = NewtonRaphsonMethod()
+        self.bus_type = None
+        self.slack = None
+        self._state_dirty = True
+        self._initial = None
+
+    # vectors kept on the device; fetched on demand
+    def _vectors(self):
+        m = self.method
+        f = np.empty(m.dim)
+        inc = np.empty(m.dim)
+        jv = np.empty(len(m.jacobian_rowval))
+        it = C.c_int64(0)
+        lib = self.ctx.lib
+        self.ctx.check(lib.jgb_nr_get_vectors(self.ctx.handle, ptr(f, C.c_double), ptr(inc, C.c_double),
+                                              ptr(jv, C.c_double), C.byref(it)))
+        return f, inc, jv, it.value
+
+    @property
+    def mismatch(self):
+        return self._vectors()[0]
+
+    @property
+    def increment(self):
+        return self._vectors()[1]
+
+    @property
+    def jacobian_nzval(self):
+        return self._vectors()[2]
+
+    def _push_state(self):
+        lib = self.ctx.lib
+        self.ctx.check(lib.jgb_nr_set_state(self.ctx.handle, ptr(f64(self.voltage.magnitude), C.c_double),
+                                            ptr(f64(self.voltage.angle), C.c_double)))
+        self._state_dirty = False
+
+    def _pull_state(self):
+        lib = self.ctx.lib
+        vm = np.empty(self.system.n)
+        va = np.empty(self.system.n)
+        self.ctx.check(lib.jgb_nr_get_state(self.ctx.handle, ptr(vm, C.c_double), ptr(va, C.c_double)))
+        self.voltage = Polar(vm, va)
+
+
+def _initialize(system: PowerSystem):
+    """initializeACPowerFlow + changeSlackBus! (acPowerFlow.jl:1312-1358), on copies."""
+    _, _, first_gen = system.supply
+    has_gen = first_gen >= 0
+    bus_type = system.bus_type.copy()
+    bus_type[(~has_gen) & (bus_type == 2)] = 1
+    vm = system.vm.copy()
+    sel = has_gen & (bus_type != 1)
+    vm[sel] = system.gen_vm[first_gen[sel]]
+    slack = system.slack
+    if not has_gen[slack]:
+        bus_type[slack] = 1
+        cand = np.flatnonzero((bus_type == 2) & has_gen)
+        if len(cand) == 0:
+            raise RuntimeError("The slack bus is missing.")
+        slack = int(cand[0])
+        bus_type[slack] = 3
+    return bus_type, slack, vm, system.va.copy()
+
+
+def newton_raphson(system: PowerSystem, ctx: Context | None = None, device: int = 0) -> AcPowerFlow:
+    if system.model is None:
+        system.model = ac_model(system)
+    mdl: AcModel = system.model
+    ctx = ctx or Context(device)
+    lib = ctx.lib
+    a = AcPowerFlow(system, ctx)
+    bus_type, slack, vm, va = _initialize(system)
+    a.bus_type, a.slack = bus_type, slack
+    ycp, yrv = i64(mdl.colptr), i64(mdl.rowval)
+    ctx.check(lib.jgb_nr_setup(ctx.handle, system.n, ptr(ycp, C.c_int64), ptr(yrv, C.c_int64),
+                               ptr(cplx(mdl.nzval), C.c_double), ptr(cplx(mdl.nzval_t), C.c_double),
+                               ptr(i8(bus_type), C.c_int8), slack + 1))
+    dim, nnz = C.c_int64(0), C.c_int64(0)
+    ctx.check(lib.jgb_nr_dims(ctx.handle, C.byref(dim), C.byref(nnz)))
+    m = a.method
+    m.dim = dim.value
+    m.pq = np.empty(system.n, dtype=np.int64)
+    m.pvpq = np.empty(system.n, dtype=np.int64)
+    m.pcount = np.empty(system.n, dtype=np.int64)
+    m.jacobian_colptr = np.empty(dim.value + 1, dtype=np.int64)
+    m.jacobian_rowval = np.empty(nnz.value, dtype=np.int64)
+    ctx.check(lib.jgb_nr_pattern(ctx.handle, ptr(m.pq, C.c_int64), ptr(m.pvpq, C.c_int64), ptr(m.pcount, C.c_int64),
+                                 ptr(m.jacobian_colptr, C.c_int64), ptr(m.jacobian_rowval, C.c_int64)))
+    sp, sq, _ = system.supply
+    ctx.check(lib.jgb_nr_set_injection(ctx.handle, ptr(f64(sp), C.c_double), ptr(f64(sq), C.c_double),
+                                       ptr(f64(system.pd), C.c_double), ptr(f64(system.qd), C.c_double)))
+    a.voltage = Polar(vm, va)
+    a._initial = (vm.copy(), va.copy())
+    a._push_state()
+    return a
+
+
+def mismatch(a: AcPowerFlow):
+    """mismatch!(analysis) -> (stopP, stopQ)."""
+    if a._state_dirty:
+        a._push_state()
+    sp, sq = C.c_double(0), C.c_double(0)
+    a.ctx.check(a.ctx.lib.jgb_nr_mismatch(a.ctx.handle, C.byref(sp), C.byref(sq)))
+    return sp.value, sq.value
+
+
+def solve(a: AcPowerFlow):
+    """solve!(analysis): Jacobian fill, refactor, solve, V/theta update, iteration += 1."""
+    if a._state_dirty:
+        a._push_state()
+    a.ctx.check(a.ctx.lib.jgb_nr_solve(a.ctx.handle))
+    a.method.iteration += 1
+    a._pull_state()
+
+
+def power_flow(a: AcPowerFlow, iteration: int = 20, tolerance: float = 1e-8) -> bool:
+    """powerFlow!(analysis; iteration, tolerance). Returns True when converged (the reference only prints it)."""
+    if a._state_dirty:
+        a._push_state()
+    it, sp, sq = C.c_int64(0), C.c_double(0), C.c_double(0)
+    rc = a.ctx.check(a.ctx.lib.jgb_nr_run(a.ctx.handle, iteration, tolerance, C.byref(it), C.byref(sp), C.byref(sq)))
+    a.method.iteration = it.value
+    a.last_stop = (sp.value, sq.value)
+    a._pull_state()
+    return rc == 0
+
+
+def set_initial_point(a: AcPowerFlow):
+    """setInitialPoint!(analysis): back to the start point of the constructor."""
+    a.voltage = Polar(a._initial[0].copy(), a._initial[1].copy())
+    a._state_dirty = True
+
+
+def set_voltage(a: AcPowerFlow, magnitude, angle):
+    a.voltage = Polar(np.array(magnitude, dtype=float), np.array(angle, dtype=float))
+    a._state_dirty = True
+
+
+def update_branch(a: AcPowerFlow, k: int, status: int):
+    """updateBranch!(analysis; label = k, status): in-place Ybus value update on the fixed pattern
+    (updateBranchMain! branch.jl:313-431 + acNodalUpdate! model.jl:81-110). k is the 0-based branch index."""
+    sysm, mdl = a.system, a.system.model
+    old = int(sysm.status[k])
+    if status == old:
+        return
+    i, j = int(sysm.frm[k]), int(sysm.to[k])
+    if status == 0:
+        dff, dft, dtf, dtt = -mdl.y_ff[k], -mdl.y_ft[k], -mdl.y_tf[k], -mdl.y_tt[k]
+    else:
+        one = sysm.copy()
+        one.status[:] = 0
+        one.status[k] = 1
+        one.model = None
+        tmp = ac_model(one)
+        dff, dft, dtf, dtt = tmp.y_ff[k], tmp.y_ft[k], tmp.y_tf[k], tmp.y_tt[k]
+        mdl.admittance[k] = tmp.admittance[k]
+    pos = [mdl.position(i, i), mdl.position(j, j), mdl.position(i, j), mdl.position(j, i)]
+    # nodalMatrix: (i,i)+=ff (j,j)+=tt (i,j)+=ft (j,i)+=tf ; transpose: (j,i) position holds Y[i,j] etc.
+    mdl.nzval[pos[0]] += dff
+    mdl.nzval[pos[1]] += dtt
+    mdl.nzval[pos[2]] += dft
+    mdl.nzval[pos[3]] += dtf
+    mdl.nzval_t[pos[0]] += dff
+    mdl.nzval_t[pos[1]] += dtt
+    mdl.nzval_t[pos[3]] += dft
+    mdl.nzval_t[pos[2]] += dtf
+    if status == 0:
+        mdl.y_ff[k] = mdl.y_ft[k] = mdl.y_tf[k] = mdl.y_tt[k] = 0
+        mdl.admittance[k] = 0
+    else:
+        mdl.y_ff[k], mdl.y_ft[k], mdl.y_tf[k], mdl.y_tt[k] = dff, dft, dtf, dtt
+    sysm.status[k] = status
+    p1 = i64(np.array(pos) + 1)
+    yv = cplx(mdl.nzval[pos])
+    ytv = cplx(mdl.nzval_t[pos])
+    a.ctx.check(a.ctx.lib.jgb_nr_update_y(a.ctx.handle, 4, ptr(p1, C.c_int64), ptr(yv, C.c_double),
+                                          ptr(ytv, C.c_double)))
+
+
+# camelCase aliases matching the reference's exported names
+newtonRaphson = newton_raphson
+powerFlow = power_flow
+setInitialPoint = set_initial_point
+updateBranch = update_branch

@@ -1,0 +1,262 @@
+// extern "C" boundary of libjgb200.so (see include/jgb200.h). Plain pointers and sizes only; every C++ exception is
+// mapped to a negative status code and a message retrievable with jgb_last_error().
+#include "../../include/jgb200.h"
+
+#include <memory>
+#include <string>
+
+#include "common.cuh"
+#include "nr.cuh"
+#include "symbolic.hpp"
+#ifdef JGB_WITH_WLS
+#include "wls.cuh"
+#endif
+
+struct jgb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    std::unique_ptr<jgb::NrContext> nr;
+#ifdef JGB_WITH_WLS
+    std::unique_ptr<jgb::WlsContext> wls;
+#endif
+};
+
+namespace {
+std::string g_create_error;
+
+template <typename F>
+int32_t guarded(jgb_ctx* ctx, F&& fn) {
+    if (!ctx) return -1;
+    try {
+        cudaError_t e = cudaSetDevice(ctx->device);
+        if (e != cudaSuccess) throw jgb::CudaError(std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+        return fn();
+    } catch (const std::invalid_argument& e) {
+        ctx->err = e.what();
+        return -1;
+    } catch (const jgb::CudaError& e) {
+        ctx->err = e.what();
+        cudaGetLastError();
+        return -2;
+    } catch (const std::domain_error& e) {
+        ctx->err = e.what();
+        return -3;
+    } catch (const std::logic_error& e) {
+        ctx->err = e.what();
+        return -1;
+    } catch (const std::exception& e) {
+        ctx->err = e.what();
+        return -4;
+    }
+}
+
+jgb::NrContext& nr_of(jgb_ctx* ctx) {
+    if (!ctx->nr) throw std::logic_error("jgb_nr_setup has not been called on this context");
+    return *ctx->nr;
+}
+}  // namespace
+
+extern "C" {
+
+int32_t jgb_abi_version(void) { return 1; }
+
+jgb_ctx* jgb_create(int32_t device, void* stream, int32_t* rc) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        g_create_error = std::string("no CUDA device available (") + cudaGetErrorString(e) +
+                         "); jgb200 has no CPU fallback";
+        cudaGetLastError();
+        if (rc) *rc = -5;
+        return nullptr;
+    }
+    if (device < 0 || device >= count) {
+        g_create_error = "device index out of range";
+        if (rc) *rc = -1;
+        return nullptr;
+    }
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess) {
+        g_create_error = std::string("cudaSetDevice: ") + cudaGetErrorString(e);
+        if (rc) *rc = -2;
+        return nullptr;
+    }
+    jgb_ctx* ctx = new jgb_ctx();
+    ctx->device = device;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            g_create_error = std::string("cudaStreamCreate: ") + cudaGetErrorString(e);
+            delete ctx;
+            if (rc) *rc = -2;
+            return nullptr;
+        }
+        ctx->own_stream = true;
+    }
+    if (rc) *rc = 0;
+    return ctx;
+}
+
+void jgb_destroy(jgb_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    ctx->nr.reset();
+#ifdef JGB_WITH_WLS
+    ctx->wls.reset();
+#endif
+    if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* jgb_last_error(const jgb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int32_t jgb_synchronize(jgb_ctx* ctx) {
+    return guarded(ctx, [&] { JGB_CUDA(cudaStreamSynchronize(ctx->stream)); return 0; });
+}
+
+int32_t jgb_nr_setup(jgb_ctx* ctx, int64_t n, const int64_t* y_colptr, const int64_t* y_rowval,
+                     const double* y_nzval, const double* yt_nzval, const int8_t* bus_type, int64_t slack) {
+    return guarded(ctx, [&] {
+        auto nr = std::make_unique<jgb::NrContext>(ctx->stream);
+        nr->setup(n, y_colptr, y_rowval, y_nzval, yt_nzval, bus_type, slack);
+        ctx->nr = std::move(nr);
+        return 0;
+    });
+}
+
+int32_t jgb_nr_dims(jgb_ctx* ctx, int64_t* dim_j, int64_t* nnz_j) {
+    return guarded(ctx, [&] {
+        auto& nr = nr_of(ctx);
+        if (dim_j) *dim_j = nr.dim;
+        if (nnz_j) *nnz_j = nr.nnzj;
+        return 0;
+    });
+}
+
+int32_t jgb_nr_pattern(jgb_ctx* ctx, int64_t* pq, int64_t* pvpq, int64_t* pcount, int64_t* j_colptr,
+                       int64_t* j_rowval) {
+    return guarded(ctx, [&] {
+        auto& nr = nr_of(ctx);
+        if (pq) std::copy(nr.pq1.begin(), nr.pq1.end(), pq);
+        if (pvpq) std::copy(nr.pvpq1.begin(), nr.pvpq1.end(), pvpq);
+        if (pcount) std::copy(nr.pcount1.begin(), nr.pcount1.end(), pcount);
+        if (j_colptr) std::copy(nr.jcolptr1.begin(), nr.jcolptr1.end(), j_colptr);
+        if (j_rowval) std::copy(nr.jrowval1.begin(), nr.jrowval1.end(), j_rowval);
+        return 0;
+    });
+}
+
+int32_t jgb_nr_set_injection(jgb_ctx* ctx, const double* ps, const double* qs, const double* pd, const double* qd) {
+    return guarded(ctx, [&] { nr_of(ctx).set_injection(ps, qs, pd, qd); return 0; });
+}
+
+int32_t jgb_nr_set_state(jgb_ctx* ctx, const double* vm, const double* va) {
+    return guarded(ctx, [&] { nr_of(ctx).set_state(vm, va); return 0; });
+}
+
+int32_t jgb_nr_get_state(jgb_ctx* ctx, double* vm, double* va) {
+    return guarded(ctx, [&] {
+        if (!vm || !va) throw std::invalid_argument("nr_get_state: null output");
+        nr_of(ctx).get_state(vm, va);
+        return 0;
+    });
+}
+
+int32_t jgb_nr_update_y(jgb_ctx* ctx, int64_t k, const int64_t* nz_pos, const double* y, const double* yt) {
+    return guarded(ctx, [&] {
+        if (k < 0 || (k > 0 && (!nz_pos || !y || !yt))) throw std::invalid_argument("nr_update_y: null input");
+        nr_of(ctx).update_y(k, nz_pos, y, yt);
+        return 0;
+    });
+}
+
+int32_t jgb_nr_mismatch(jgb_ctx* ctx, double* stop_p, double* stop_q) {
+    return guarded(ctx, [&] { nr_of(ctx).mismatch(stop_p, stop_q); return 0; });
+}
+
+int32_t jgb_nr_solve(jgb_ctx* ctx) {
+    return guarded(ctx, [&] { nr_of(ctx).solve(); return 0; });
+}
+
+int32_t jgb_nr_get_vectors(jgb_ctx* ctx, double* mismatch, double* increment, double* j_nzval, int64_t* iteration) {
+    return guarded(ctx, [&] { nr_of(ctx).get_vectors(mismatch, increment, j_nzval, iteration); return 0; });
+}
+
+int32_t jgb_nr_run(jgb_ctx* ctx, int64_t max_iter, double tol, int64_t* iterations, double* stop_p, double* stop_q) {
+    return guarded(ctx, [&] {
+        if (max_iter < 0) throw std::invalid_argument("nr_run: negative iteration cap");
+        return nr_of(ctx).run(max_iter, tol, iterations, stop_p, stop_q);
+    });
+}
+
+int32_t jgb_nr_batch(jgb_ctx* ctx, int64_t S, const int64_t* out_from, const int64_t* out_to, const double* dy,
+                     int64_t max_iter, double tol, double* vm_out, double* va_out, int32_t* iterations,
+                     int8_t* status, int64_t* total_iterations) {
+    return guarded(ctx, [&] {
+        if (!vm_out || !va_out) throw std::invalid_argument("nr_batch: null output");
+        return nr_of(ctx).batch(S, out_from, out_to, dy, false, max_iter, tol, vm_out, va_out, iterations, status,
+                                false, total_iterations);
+    });
+}
+
+int32_t jgb_nr_batch_dev(jgb_ctx* ctx, int64_t S, const int64_t* out_from, const int64_t* out_to, const double* dy,
+                         int64_t max_iter, double tol, double* vm_out, double* va_out, int32_t* iterations,
+                         int8_t* status, int64_t* total_iterations) {
+    return guarded(ctx, [&] {
+        if (!vm_out || !va_out || !iterations || !status) throw std::invalid_argument("nr_batch_dev: null output");
+        return nr_of(ctx).batch(S, out_from, out_to, dy, true, max_iter, tol, vm_out, va_out, iterations, status,
+                                true, total_iterations);
+    });
+}
+
+double jgb_stat(jgb_ctx* ctx, const char* key) {
+    if (!ctx || !key) return -1.0;
+    try {
+        std::string k(key);
+        if (k == "launches") {
+            double t = 0;
+            if (ctx->nr) t += (double)ctx->nr->launches;
+#ifdef JGB_WITH_WLS
+            if (ctx->wls) t += (double)ctx->wls->launches;
+#endif
+            return t;
+        }
+        if (k.rfind("nr.", 0) == 0 && ctx->nr) return ctx->nr->stat(k);
+#ifdef JGB_WITH_WLS
+        if (k.rfind("wls.", 0) == 0 && ctx->wls) return ctx->wls->stat(k);
+#endif
+    } catch (...) {
+    }
+    return -1.0;
+}
+
+int32_t jgb_selfcheck_symbolic(int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                               const int64_t* group, const double* rhs, double* x, double* stats8) {
+    try {
+        if (n <= 0 || !colptr || !rowval) return -1;
+        std::vector<int> cp(n + 1), rv(colptr[n] - 1), grp;
+        for (int64_t i = 0; i <= n; ++i) cp[i] = (int)(colptr[i] - 1);
+        for (size_t q = 0; q < rv.size(); ++q) rv[q] = (int)(rowval[q] - 1);
+        if (group) {
+            grp.resize(n);
+            for (int64_t i = 0; i < n; ++i) grp[i] = (int)group[i];
+        }
+        jgb::Symbolic s;
+        jgb::analyse((int)n, cp.data(), rv.data(), group ? grp.data() : nullptr, nullptr, jgb::SymbolicOptions(), s);
+        if (stats8) {
+            stats8[0] = s.nfronts; stats8[1] = s.nlevels; stats8[2] = s.ndepths; stats8[3] = (double)s.nnz_lu;
+            stats8[4] = s.flops; stats8[5] = s.max_front; stats8[6] = (double)s.u_size; stats8[7] = (double)s.upd_size;
+        }
+        if (nzval && rhs && x) return jgb::host_factor_solve(s, nzval, rhs, x);
+        return 0;
+    } catch (...) {
+        return -4;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,57 @@
+// Fixed-pattern multifrontal LU (no pivoting, right-hand side carried as an extra front column) on the GPU.
+//
+// Replaces the numeric half of the reference's `factorization!` + `solution!`
+// (src/backend/utility.jl:478-500, 542-548, 576-586 -> UMFPACK / KLU / CHOLMOD in the reference).
+// One instance owns the device copy of a `Symbolic` and the factor workspaces for up to S scenarios;
+// values are laid out scenario-minor: element e of scenario s lives at [e * S + s].
+#pragma once
+#include "common.cuh"
+#include "symbolic.hpp"
+
+namespace jgb {
+
+struct DevSym {
+    const int *f_k, *f_nf, *f_rowptr, *f_rows, *f_relptr, *f_rel, *f_childptr, *f_children, *f_asmptr, *asm_src,
+        *asm_dst;
+    const long long *f_uoff, *f_updoff;
+};
+
+struct FactorLaunch {
+    int begin, count;      // range in level_fronts
+    int ts;                // scenarios per CTA
+    int threads;
+    int tr;                // row lanes (power of two), column lanes = threads / ts / tr
+    size_t smem;
+};
+
+struct SolveLaunch {
+    int begin, count;      // range in depth_fronts
+    int max_nf, max_k;
+    size_t smem;           // S == 1 path only
+};
+
+class MfSolver {
+  public:
+    Symbolic sym;
+
+    void setup(const Symbolic& s, cudaStream_t st);
+    // Factor A (values `aval`, CSC order of the analysed pattern, [nnz][S]) and solve A x = rhs for every scenario.
+    // `active` (nullable, [S]) skips scenarios whose flag is 0. `status[s]` is set to -3 on a zero / non-finite pivot.
+    void factor_solve(const double* aval, const double* rhs, double* x, int S, const unsigned char* active,
+                      int* status, cudaStream_t st);
+    int64_t factor_bytes(int S) const;     // algorithmic HBM bytes of one factor_solve (for roofline reports)
+    int launches_per_solve(int S);
+
+  private:
+    void plan(int S);
+    int planned_S = -1;
+    std::vector<FactorLaunch> fplan;
+    std::vector<SolveLaunch> splan;
+    DevBuf<int> d_f_k, d_f_nf, d_f_rowptr, d_f_rows, d_f_relptr, d_f_rel, d_f_childptr, d_f_children, d_f_asmptr,
+        d_asm_src, d_asm_dst, d_level_fronts, d_depth_fronts;
+    DevBuf<long long> d_f_uoff, d_f_updoff;
+    DevBuf<double> d_U, d_upd;
+    DevSym dev{};
+};
+
+}  // namespace jgb

@@ -1,0 +1,71 @@
+// Symbolic analysis for the fixed-pattern multifrontal solver (host side, done once per topology).
+//
+// Replaces the symbolic half of what the reference gets from SuiteSparse through
+// `factorization(...)` (src/backend/utility.jl:470-476, 534-540): fill-reducing ordering,
+// elimination tree, supernodes (= fronts), assembly maps and the level schedules that the
+// numeric kernels (solver.cu) replay at every Newton / Gauss-Newton iteration
+// (`factorization!`, utility.jl:478-484 / 542-548) and for every scenario of a batch.
+#pragma once
+#include <cstdint>
+#include <vector>
+
+namespace jgb {
+
+struct SymbolicOptions {
+    int relax_small = 4;      // always merge a last child into its parent if the merged pivot count <= this
+    int relax_mid = 16;       // merge up to this many pivots if the zero fraction stays below relax_mid_frac
+    double relax_mid_frac = 0.5;
+    int relax_big = 48;
+    double relax_big_frac = 0.15;
+    double relax_any_frac = 0.05;
+};
+
+struct Symbolic {
+    int n = 0;                       // scalar dimension
+    std::vector<int> perm;           // elimination position -> original variable
+    std::vector<int> iperm;          // original variable -> elimination position
+
+    int nfronts = 0;
+    std::vector<int> f_k;            // pivots per front
+    std::vector<int> f_nf;           // front order (pivots + update rows)
+    std::vector<int> f_rowptr;       // [nfronts+1] offsets into f_rows
+    std::vector<int> f_rows;         // ORIGINAL variable ids of the front rows; first k are the pivots
+    std::vector<int> f_parent;       // parent front or -1
+    std::vector<int> f_relptr;       // [nfronts+1] offsets into f_rel (one per update row)
+    std::vector<int> f_rel;          // position of each update row in the parent's row list
+    std::vector<int> f_childptr;     // [nfronts+1]
+    std::vector<int> f_children;
+    std::vector<int> f_asmptr;       // [nfronts+1] offsets into asm_src/asm_dst
+    std::vector<int> asm_src;        // index into the matrix's CSC nzval
+    std::vector<int> asm_dst;        // r + c*nf inside the front (column major, leading dimension nf)
+    std::vector<int64_t> f_uoff;     // offset of the front's packed U rows (k rows, row p has nf+1-p entries)
+    std::vector<int64_t> f_updoff;   // offset of the front's update block (u x (u+1), column major, last col = rhs)
+    int64_t u_size = 0, upd_size = 0;
+
+    // schedules
+    int nlevels = 0;                 // factor levels: leaves first
+    std::vector<int> levelptr;       // [nlevels+1]
+    std::vector<int> level_fronts;   // fronts grouped by height level (sorted by decreasing nf inside a level)
+    int ndepths = 0;                 // back-solve levels: roots first
+    std::vector<int> depthptr;
+    std::vector<int> depth_fronts;
+
+    // statistics
+    int64_t nnz_lu = 0;              // scalar nnz(L+U) incl. diagonal, with amalgamation zeros
+    double flops = 0;                // factorisation flops (LU)
+    int max_front = 0;
+};
+
+// Pattern: CSC of an n x n matrix (0-based). `group[v]` (may be null) ties variables that must stay adjacent
+// in the ordering (theta_i / V_i of one bus). The pattern is symmetrised (A + A') internally; entries of A that
+// are structurally absent from A' simply stay zero in the fronts.
+// `skip[v] != 0` (may be null) marks variables whose row/column is identity (WLS slack angle): they are ordered
+// last as isolated 1x1 fronts and entries touching them are ignored by the assembly map.
+void analyse(int n, const int* colptr, const int* rowidx, const int* group, const unsigned char* skip,
+             const SymbolicOptions& opt, Symbolic& out);
+
+// Host reference of the numeric phase (S = 1): used by the CPU self-check tests of the symbolic data
+// only — never by the operators. Returns 0, or -3 on a zero pivot.
+int host_factor_solve(const Symbolic& s, const double* aval, const double* rhs, double* x);
+
+}  // namespace jgb

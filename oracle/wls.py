@@ -73,7 +73,7 @@ def _push(dev: dict, **kw):
 def measurements_from_solution(sys: System, pw: dict, vm: np.ndarray, va: np.ndarray, *,
                                volt=True, watt=True, var=True, amp=False, amp_square=False,
                                pmu_bus=(), pmu_branch=False, pmu_polar=True, pmu_square=False,
-                               pmu_correlated=False,
+                               pmu_correlated=False, power_bus=True, power_branch=True,
                                var_volt=1e-4, var_power=1e-4, var_amp=1e-4, var_pmu_mag=1e-8, var_pmu_ang=1e-8
                                ) -> Measurement:
     """Exact measurement set from a solved state, in the row order the reference's generators produce:
@@ -96,9 +96,9 @@ def measurements_from_solution(sys: System, pw: dict, vm: np.ndarray, va: np.nda
                                    (var, m.var, "injection_reactive", "from_reactive", "to_reactive")):
         if not flag:
             continue
-        for i in range(sys.n):
+        for i in range(sys.n if power_bus else 0):
             _push(dev, index=i, bus=True, frm=False, mean=pw[inj][i], variance=var_power, status=1)
-        for k in on:
+        for k in (on if power_branch else ()):
             _push(dev, index=k, bus=False, frm=True, mean=pw[fr][k], variance=var_power, status=1)
             _push(dev, index=k, bus=False, frm=False, mean=pw[to][k], variance=var_power, status=1)
     for i in pmu_bus:
