@@ -80,6 +80,48 @@ int32_t jgb_nr_batch_dev(jgb_ctx* ctx, int64_t S, const int64_t* out_from_dev, c
                          const double* dy_dev, int64_t max_iter, double tol, double* vm_out_dev, double* va_out_dev,
                          int32_t* iterations_dev, int8_t* status_dev, int64_t* total_iterations);
 
+/* ---- Gauss-Newton WLS AC state estimation ---------------------------------------------------------------------- */
+/* gaussNewton(monitoring) after acWLS (acStateEstimation.jl:43-259): takes the tables acWLS builds — the CSC pattern
+ * of the Jacobian H (m x 2n; theta columns 1..n, V columns n+1..2n), type (Int8 codes 0..21), index (bus or branch),
+ * range (6 row offsets), the precision matrix W (CSC; diagonal or 2x2 blocks for correlated rectangular PMUs) —
+ * plus Ybus / Ybus transpose, branch.layout.from/to, branch.parameter.conductance/susceptance/turnsRatio/shiftAngle
+ * and model.ac.admittance (ComplexF64).  Builds the pattern of G = H'WH, its gather lists and symbolic factorisation. */
+int32_t jgb_wls_setup(jgb_ctx* ctx, int64_t n, int64_t m, int64_t slack, const int64_t* h_colptr,
+                      const int64_t* h_rowval, const int8_t* type, const int64_t* index, const int64_t* range6,
+                      const int64_t* w_colptr, const int64_t* w_rowval, const double* w_nzval,
+                      const int64_t* y_colptr, const int64_t* y_rowval, const double* y_nzval_re_im,
+                      const double* yt_nzval_re_im, int64_t nbranch, const int64_t* from, const int64_t* to,
+                      const double* conductance, const double* susceptance, const double* turns_ratio,
+                      const double* shift_angle, const double* admittance_re_im);
+int32_t jgb_wls_dims(jgb_ctx* ctx, int64_t* nnz_h, int64_t* nnz_g);
+/* CSC pattern (1-based) of the gain matrix as Julia's `transpose(H) * W * H` stores it (slack row/column kept) */
+int32_t jgb_wls_gain_pattern(jgb_ctx* ctx, int64_t* g_colptr, int64_t* g_rowval);
+/* method.mean (length m) */
+int32_t jgb_wls_set_mean(jgb_ctx* ctx, const double* z);
+int32_t jgb_wls_set_state(jgb_ctx* ctx, const double* vm, const double* va);
+int32_t jgb_wls_get_state(jgb_ctx* ctx, double* vm, double* va);
+/* increment!(analysis) (acStateEstimation.jl:878-904): normalEquation!, G = H'WH with the slack fix, refactor,
+ * solve, increment[slack] = 0 -> returns maximum(abs, increment); *objective = method.objective */
+int32_t jgb_wls_increment(jgb_ctx* ctx, double* max_increment, double* objective);
+/* solve!(analysis) (acStateEstimation.jl:1035-1047): theta += d[1:n], V += d[n+1:2n], iteration += 1 */
+int32_t jgb_wls_solve(jgb_ctx* ctx);
+/* method.residual (m), method.increment (2n), method.jacobian.nzval (CSC order of h_colptr/h_rowval), gain values
+ * (CSC order of jgb_wls_gain_pattern), method.iteration; any pointer may be NULL */
+int32_t jgb_wls_get_vectors(jgb_ctx* ctx, double* residual, double* increment, double* h_nzval, double* g_nzval,
+                            int64_t* iteration);
+/* stateEstimation!(analysis; iteration, tolerance) loop (acStateEstimation.jl:1286-1329). 0 converged / 1 cap. */
+int32_t jgb_wls_run(jgb_ctx* ctx, int64_t max_iter, double tol, int64_t* iterations, double* max_increment,
+                    double* objective);
+/* S independent estimations on one topology / measurement layout differing only in the means (Monte-Carlo draws):
+ * Z is S x m row-major; every draw starts from the state last set with jgb_wls_set_state. Outputs S x n row-major. */
+int32_t jgb_wls_batch(jgb_ctx* ctx, int64_t S, const double* Z, int64_t max_iter, double tol, double* vm_out,
+                      double* va_out, int32_t* iterations, int8_t* status, double* objective,
+                      int64_t* total_iterations);
+/* Same with DEVICE pointers for Z and all outputs. */
+int32_t jgb_wls_batch_dev(jgb_ctx* ctx, int64_t S, const double* Z_dev, int64_t max_iter, double tol,
+                          double* vm_out_dev, double* va_out_dev, int32_t* iterations_dev, int8_t* status_dev,
+                          double* objective_dev, int64_t* total_iterations);
+
 /* ---- statistics for roofline reports ------------------------------------------------------------------------ */
 /* key: "nr.nnz_lu", "nr.fronts", "nr.levels", "nr.flops", "nr.max_front", "nr.launches_per_iteration",
  *      "nr.assemble_bytes" (per scenario-iteration), "nr.solve_bytes", "wls.*" likewise; kernel launch counter

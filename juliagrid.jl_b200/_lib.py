@@ -80,8 +80,6 @@ def load() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     for table in (PROTOTYPES, WLS_PROTOTYPES):
         for name, (res, args) in table.items():
-            if table is WLS_PROTOTYPES and not hasattr(lib, name):   # TEMPORARY until wls.cu lands
-                continue
             fn = getattr(lib, name)   # AttributeError here = header / library mismatch
             fn.restype = res
             fn.argtypes = args

@@ -1,0 +1,146 @@
+"""Host mirror of the reference's Gauss-Newton WLS operator surface, backed by libjgb200.so.
+
+    gauss_newton(monitoring)         <-> gaussNewton(monitoring, B200)   src/stateEstimation/acStateEstimation.jl:43-75
+    increment(analysis)              <-> increment!(analysis)            :878-904
+    solve_se(analysis)               <-> solve!(analysis)                :1035-1047
+    state_estimation(analysis; ...)  <-> stateEstimation!(analysis; ...) :1286-1329
+    set_mean(analysis, z)            <-> update*!(analysis; ...) value updates (measurement/*.jl), pattern fixed
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from ._lib import Context, ptr, f64, i64, i8, cplx
+from .ac_power_flow import Polar
+from .measurement import Measurement, WlsTables, ac_wls
+from .model import ac_model
+
+
+class GaussNewtonMethod:
+    """analysis.method — host mirrors of GaussNewton{T} (src/definition/analysis.jl:532-545)."""
+
+    def __init__(self):
+        self.tables: WlsTables = None
+        self.mean = None
+        self.type = None
+        self.index = None
+        self.range = None
+        self.gain_colptr = self.gain_rowval = None
+        self.objective = 0.0
+        self.iteration = 0
+
+
+class AcStateEstimation:
+    def __init__(self, monitoring: Measurement, ctx: Context):
+        self.monitoring = monitoring
+        self.system = monitoring.system
+        self.ctx = ctx
+        self.voltage: Polar = None
+        self.method = GaussNewtonMethod()
+        self._dirty = True
+
+    def _vectors(self):
+        t = self.method.tables
+        n = self.system.n
+        res, inc = np.empty(t.m), np.empty(2 * n)
+        hv = np.empty(len(t.h_rowval))
+        gv = np.empty(len(self.method.gain_rowval))
+        it = C.c_int64(0)
+        self.ctx.check(self.ctx.lib.jgb_wls_get_vectors(self.ctx.handle, ptr(res, C.c_double), ptr(inc, C.c_double),
+                                                        ptr(hv, C.c_double), ptr(gv, C.c_double), C.byref(it)))
+        return res, inc, hv, gv
+
+    residual = property(lambda self: self._vectors()[0])
+    increment = property(lambda self: self._vectors()[1])
+    jacobian_nzval = property(lambda self: self._vectors()[2])
+    gain_nzval = property(lambda self: self._vectors()[3])
+
+    def _push(self):
+        self.ctx.check(self.ctx.lib.jgb_wls_set_state(self.ctx.handle, ptr(f64(self.voltage.magnitude), C.c_double),
+                                                      ptr(f64(self.voltage.angle), C.c_double)))
+        self._dirty = False
+
+    def _pull(self):
+        vm, va = np.empty(self.system.n), np.empty(self.system.n)
+        self.ctx.check(self.ctx.lib.jgb_wls_get_state(self.ctx.handle, ptr(vm, C.c_double), ptr(va, C.c_double)))
+        self.voltage = Polar(vm, va)
+
+
+def gauss_newton(monitoring: Measurement, ctx: Context | None = None, device: int = 0) -> AcStateEstimation:
+    system = monitoring.system
+    if system.model is None:
+        system.model = ac_model(system)
+    mdl = system.model
+    ctx = ctx or Context(device)
+    a = AcStateEstimation(monitoring, ctx)
+    t = ac_wls(system, monitoring)
+    lib = ctx.lib
+    P = lambda v, ct: ptr(v, ct)
+    hcp, hrv, idx, rng = i64(t.h_colptr), i64(t.h_rowval), i64(t.index), i64(t.range)
+    wcp, wrv, wnz = i64(t.w_colptr), i64(t.w_rowval), f64(t.w_nzval)
+    ycp, yrv = i64(mdl.colptr), i64(mdl.rowval)
+    frm, to = i64(system.frm + 1), i64(system.to + 1)
+    ctx.check(lib.jgb_wls_setup(
+        ctx.handle, system.n, t.m, system.slack + 1, P(hcp, C.c_int64), P(hrv, C.c_int64), P(i8(t.type), C.c_int8),
+        P(idx, C.c_int64), P(rng, C.c_int64), P(wcp, C.c_int64), P(wrv, C.c_int64), P(wnz, C.c_double),
+        P(ycp, C.c_int64), P(yrv, C.c_int64), P(cplx(mdl.nzval), C.c_double), P(cplx(mdl.nzval_t), C.c_double),
+        system.nbr, P(frm, C.c_int64), P(to, C.c_int64), P(f64(system.g), C.c_double), P(f64(system.b), C.c_double),
+        P(f64(system.tap), C.c_double), P(f64(system.shift), C.c_double), P(cplx(mdl.admittance), C.c_double)))
+    nh, ng = C.c_int64(0), C.c_int64(0)
+    ctx.check(lib.jgb_wls_dims(ctx.handle, C.byref(nh), C.byref(ng)))
+    me = a.method
+    me.tables, me.mean, me.type, me.index, me.range = t, t.mean.copy(), t.type, t.index, t.range
+    me.gain_colptr = np.empty(2 * system.n + 1, dtype=np.int64)
+    me.gain_rowval = np.empty(ng.value, dtype=np.int64)
+    ctx.check(lib.jgb_wls_gain_pattern(ctx.handle, P(me.gain_colptr, C.c_int64), P(me.gain_rowval, C.c_int64)))
+    ctx.check(lib.jgb_wls_set_mean(ctx.handle, P(f64(me.mean), C.c_double)))
+    # GN starts from bus.voltage.{magnitude, angle} (acStateEstimation.jl:52-55), not generator set-points
+    a.voltage = Polar(system.vm.copy(), system.va.copy())
+    a._push()
+    return a
+
+
+def increment(a: AcStateEstimation) -> float:
+    """increment!(analysis) -> maximum(abs, increment); sets method.objective."""
+    if a._dirty:
+        a._push()
+    mi, ob = C.c_double(0), C.c_double(0)
+    a.ctx.check(a.ctx.lib.jgb_wls_increment(a.ctx.handle, C.byref(mi), C.byref(ob)))
+    a.method.objective = ob.value
+    return mi.value
+
+
+def solve_se(a: AcStateEstimation):
+    """solve!(analysis)."""
+    a.ctx.check(a.ctx.lib.jgb_wls_solve(a.ctx.handle))
+    a.method.iteration += 1
+    a._pull()
+
+
+def state_estimation(a: AcStateEstimation, iteration: int = 40, tolerance: float = 1e-8) -> bool:
+    """stateEstimation!(analysis; iteration, tolerance); True when converged."""
+    if a._dirty:
+        a._push()
+    it, mi, ob = C.c_int64(0), C.c_double(0), C.c_double(0)
+    rc = a.ctx.check(a.ctx.lib.jgb_wls_run(a.ctx.handle, iteration, tolerance, C.byref(it), C.byref(mi), C.byref(ob)))
+    a.method.iteration = it.value
+    a.method.objective = ob.value
+    a.last_increment = mi.value
+    a._pull()
+    return rc == 0
+
+
+def set_mean(a: AcStateEstimation, z):
+    a.method.mean = np.array(z, dtype=float)
+    a.ctx.check(a.ctx.lib.jgb_wls_set_mean(a.ctx.handle, ptr(f64(a.method.mean), C.c_double)))
+
+
+def set_voltage_se(a: AcStateEstimation, magnitude, angle):
+    a.voltage = Polar(np.array(magnitude, dtype=float), np.array(angle, dtype=float))
+    a._dirty = True
+
+
+gaussNewton = gauss_newton
+stateEstimation = state_estimation

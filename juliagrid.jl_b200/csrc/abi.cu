@@ -214,6 +214,107 @@ int32_t jgb_nr_batch_dev(jgb_ctx* ctx, int64_t S, const int64_t* out_from, const
     });
 }
 
+#ifdef JGB_WITH_WLS
+namespace {
+jgb::WlsContext& wls_of(jgb_ctx* ctx) {
+    if (!ctx->wls) throw std::logic_error("jgb_wls_setup has not been called on this context");
+    return *ctx->wls;
+}
+}  // namespace
+
+int32_t jgb_wls_setup(jgb_ctx* ctx, int64_t n, int64_t m, int64_t slack, const int64_t* h_colptr,
+                      const int64_t* h_rowval, const int8_t* type, const int64_t* index, const int64_t* range6,
+                      const int64_t* w_colptr, const int64_t* w_rowval, const double* w_nzval,
+                      const int64_t* y_colptr, const int64_t* y_rowval, const double* y_nzval, const double* yt_nzval,
+                      int64_t nbranch, const int64_t* from, const int64_t* to, const double* conductance,
+                      const double* susceptance, const double* turns_ratio, const double* shift_angle,
+                      const double* admittance) {
+    return guarded(ctx, [&] {
+        auto w = std::make_unique<jgb::WlsContext>(ctx->stream);
+        w->setup(n, m, slack, h_colptr, h_rowval, type, index, range6, w_colptr, w_rowval, w_nzval, y_colptr,
+                 y_rowval, y_nzval, yt_nzval, nbranch, from, to, conductance, susceptance, turns_ratio, shift_angle,
+                 admittance);
+        ctx->wls = std::move(w);
+        return 0;
+    });
+}
+
+int32_t jgb_wls_dims(jgb_ctx* ctx, int64_t* nnz_h, int64_t* nnz_g) {
+    return guarded(ctx, [&] {
+        auto& w = wls_of(ctx);
+        if (nnz_h) *nnz_h = w.nnzh;
+        if (nnz_g) *nnz_g = w.nnzg;
+        return 0;
+    });
+}
+
+int32_t jgb_wls_gain_pattern(jgb_ctx* ctx, int64_t* g_colptr, int64_t* g_rowval) {
+    return guarded(ctx, [&] {
+        auto& w = wls_of(ctx);
+        if (g_colptr) std::copy(w.gcolptr1.begin(), w.gcolptr1.end(), g_colptr);
+        if (g_rowval) std::copy(w.growval1.begin(), w.growval1.end(), g_rowval);
+        return 0;
+    });
+}
+
+int32_t jgb_wls_set_mean(jgb_ctx* ctx, const double* z) {
+    return guarded(ctx, [&] { wls_of(ctx).set_mean(z); return 0; });
+}
+
+int32_t jgb_wls_set_state(jgb_ctx* ctx, const double* vm, const double* va) {
+    return guarded(ctx, [&] { wls_of(ctx).set_state(vm, va); return 0; });
+}
+
+int32_t jgb_wls_get_state(jgb_ctx* ctx, double* vm, double* va) {
+    return guarded(ctx, [&] {
+        if (!vm || !va) throw std::invalid_argument("wls_get_state: null output");
+        wls_of(ctx).get_state(vm, va);
+        return 0;
+    });
+}
+
+int32_t jgb_wls_increment(jgb_ctx* ctx, double* max_increment, double* objective) {
+    return guarded(ctx, [&] { wls_of(ctx).increment(max_increment, objective); return 0; });
+}
+
+int32_t jgb_wls_solve(jgb_ctx* ctx) {
+    return guarded(ctx, [&] { wls_of(ctx).solve(); return 0; });
+}
+
+int32_t jgb_wls_get_vectors(jgb_ctx* ctx, double* residual, double* increment, double* h_nzval, double* g_nzval,
+                            int64_t* iteration) {
+    return guarded(ctx, [&] { wls_of(ctx).get_vectors(residual, increment, h_nzval, g_nzval, iteration); return 0; });
+}
+
+int32_t jgb_wls_run(jgb_ctx* ctx, int64_t max_iter, double tol, int64_t* iterations, double* max_increment,
+                    double* objective) {
+    return guarded(ctx, [&] {
+        if (max_iter < 0) throw std::invalid_argument("wls_run: negative iteration cap");
+        return wls_of(ctx).run(max_iter, tol, iterations, max_increment, objective);
+    });
+}
+
+int32_t jgb_wls_batch(jgb_ctx* ctx, int64_t S, const double* Z, int64_t max_iter, double tol, double* vm_out,
+                      double* va_out, int32_t* iterations, int8_t* status, double* objective,
+                      int64_t* total_iterations) {
+    return guarded(ctx, [&] {
+        if (!vm_out || !va_out) throw std::invalid_argument("wls_batch: null output");
+        return wls_of(ctx).batch(S, Z, false, max_iter, tol, vm_out, va_out, iterations, status, objective, false,
+                                 total_iterations);
+    });
+}
+
+int32_t jgb_wls_batch_dev(jgb_ctx* ctx, int64_t S, const double* Z, int64_t max_iter, double tol, double* vm_out,
+                          double* va_out, int32_t* iterations, int8_t* status, double* objective,
+                          int64_t* total_iterations) {
+    return guarded(ctx, [&] {
+        if (!vm_out || !va_out || !iterations || !status) throw std::invalid_argument("wls_batch_dev: null output");
+        return wls_of(ctx).batch(S, Z, true, max_iter, tol, vm_out, va_out, iterations, status, objective, true,
+                                 total_iterations);
+    });
+}
+#endif  // JGB_WITH_WLS
+
 double jgb_stat(jgb_ctx* ctx, const char* key) {
     if (!ctx || !key) return -1.0;
     try {

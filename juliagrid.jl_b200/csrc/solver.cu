@@ -22,8 +22,11 @@ __device__ __forceinline__ long long urow_off(int p, int nf) {
 __global__ void __launch_bounds__(256)
 mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ aval,
                  const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S, int TS,
-                 int TR, const unsigned char* __restrict__ active, int* __restrict__ status) {
-    extern __shared__ double F[];
+                 int TR, const unsigned char* __restrict__ active, int* __restrict__ status, double* gwork,
+                 long long gstride) {
+    extern __shared__ double Fs[];
+    // fronts too large for shared memory live in a per-CTA global (L2-resident) workspace
+    double* F = gwork ? gwork + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * gstride : Fs;
     const int f = fronts[blockIdx.x];
     const int sl = threadIdx.x % TS;
     const int e0 = threadIdx.x / TS;
@@ -88,10 +91,11 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __rest
             Cf[(long long)(i + j * u) * S] = F[((k + i) + (k + j) * nf) * TS + sl];
 }
 
-// Backward substitution, S == 1: one CTA per front. The packed U rows and the already known x of the update rows
-// are staged in shared memory; phase A removes the update-row part for all pivots in parallel, phase B runs the
-// k x k triangular solve inside warp 0.
-__global__ void __launch_bounds__(64)
+// Backward substitution, S == 1: one CTA per front, pivots processed in blocks of 32 rows from the bottom up.
+// For each block the packed U rows are staged in shared memory, the part of every row that multiplies already
+// known x (later pivots and update rows) is removed by one warp per row, and warp 0 finishes the 32 x 32 triangle.
+constexpr int kBsRows = 32;
+__global__ void __launch_bounds__(128)
 mf_backsolve_single(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ U,
                     double* __restrict__ x, const unsigned char* __restrict__ active) {
     extern __shared__ double sh[];
@@ -99,34 +103,43 @@ mf_backsolve_single(DevSym sy, const int* __restrict__ fronts, const double* __r
     const int f = fronts[blockIdx.x];
     const int nf = sy.f_nf[f], k = sy.f_k[f];
     const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
-    const int usz = (int)urow_off(k, nf);
-    double* Us = sh;             // packed rows
-    double* xs = sh + usz;       // nf entries: [0,k) = t_p then x_p, [k,nf) = x of update rows
+    double* xs = sh;              // nf entries: x of the front rows (pivots filled in as they are solved)
+    double* Us = sh + nf;         // packed rows of the current block
     const double* __restrict__ Uf = U + sy.f_uoff[f];
-    for (int e = threadIdx.x; e < usz; e += blockDim.x) Us[e] = Uf[e];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int j = k + threadIdx.x; j < nf; j += blockDim.x) xs[j] = x[rows[j]];
-    __syncthreads();
-    for (int p = threadIdx.x; p < k; p += blockDim.x) {
-        const double* Urow = Us + urow_off(p, nf);
-        double acc = Urow[nf - p];
-        for (int j = k; j < nf; ++j) acc -= Urow[j - p] * xs[j];
-        xs[p] = acc;
-    }
-    __syncthreads();
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        for (int p = k - 1; p >= 0; --p) {
-            double xp = 0.0;
-            if (lane == (p & 31)) {
-                xp = xs[p] * Us[urow_off(p, nf)];
-                xs[p] = xp;
-            }
-            xp = __shfl_sync(0xffffffffu, xp, p & 31);
-            for (int q = lane; q < p; q += 32) xs[q] -= Us[urow_off(q, nf) + (p - q)] * xp;
-            __syncwarp();
+    for (int p1 = k; p1 > 0; p1 -= kBsRows) {
+        const int p0 = max(0, p1 - kBsRows);
+        const long long base = urow_off(p0, nf);
+        const int cnt = (int)(urow_off(p1, nf) - base);
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) Us[e] = Uf[base + e];
+        __syncthreads();
+        // rows p0..p1-1: t_p = y_p - sum_{j >= p1} U[p,j] x_j
+        for (int p = p0 + warp; p < p1; p += nwarps) {
+            const double* Urow = Us + (urow_off(p, nf) - base);
+            double acc = 0.0;
+            for (int j = p1 + lane; j < nf; j += 32) acc += Urow[j - p] * xs[j];
+            for (int o = 16; o >= 1; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0) xs[p] = Urow[nf - p] - acc;
         }
-        for (int p = lane; p < k; p += 32) x[rows[p]] = xs[p];
+        __syncthreads();
+        if (warp == 0) {
+            for (int p = p1 - 1; p >= p0; --p) {
+                const int owner = (p - p0) & 31;
+                double xp = 0.0;
+                if (lane == owner) {
+                    xp = xs[p] * Us[urow_off(p, nf) - base];
+                    xs[p] = xp;
+                }
+                xp = __shfl_sync(0xffffffffu, xp, owner);
+                const int q = p0 + lane;
+                if (q < p) xs[q] -= Us[(urow_off(q, nf) - base) + (p - q)] * xp;
+                __syncwarp();
+            }
+        }
+        __syncthreads();
     }
+    for (int p = threadIdx.x; p < k; p += blockDim.x) x[rows[p]] = xs[p];
 }
 
 // Backward substitution, batch: one thread per (front, scenario); lanes of a warp are consecutive scenarios, so every
@@ -150,6 +163,8 @@ mf_backsolve_batch(DevSym sy, const int* __restrict__ fronts, int nfr, const dou
         x[(long long)rows[p] * S + s] = acc * Urow[0];
     }
 }
+
+constexpr int kMaxSmemFront = 150;    // nf*(nf+1)*8 bytes must fit the 200 KB dynamic shared-memory budget
 
 int pow2_floor(int v) {
     int p = 1;
@@ -191,7 +206,8 @@ void MfSolver::plan(int S) {
     if (S == planned_S) return;
     fplan.clear();
     splan.clear();
-    const int cls_bound[] = {6, 16, 48, 1 << 30};
+    size_t gwork_need = 0;
+    const int cls_bound[] = {6, 16, 48, kMaxSmemFront, 1 << 30};
     auto cls = [&](int nf) { int c = 0; while (nf > cls_bound[c]) ++c; return c; };
     for (int l = 0; l < sym.nlevels; ++l) {
         int b = sym.levelptr[l], e = sym.levelptr[l + 1];
@@ -205,7 +221,11 @@ void MfSolver::plan(int S) {
             FactorLaunch fl{};
             fl.begin = i;
             fl.count = j - i;
-            if (S == 1) {
+            fl.global_front = nf > kMaxSmemFront;
+            if (fl.global_front) {
+                fl.ts = (S == 1) ? 1 : 4;
+                fl.threads = 256;
+            } else if (S == 1) {
                 fl.ts = 1;
                 fl.threads = nf <= 6 ? 32 : nf <= 16 ? 64 : nf <= 48 ? 128 : 256;
             } else {
@@ -217,7 +237,10 @@ void MfSolver::plan(int S) {
             }
             int te = fl.threads / fl.ts;
             fl.tr = std::min(te, 16);
-            fl.smem = per * fl.ts;
+            fl.smem = fl.global_front ? 0 : per * fl.ts;
+            fl.gstride = (long long)nf * (nf + 1) * fl.ts;
+            if (fl.global_front)
+                gwork_need = std::max<size_t>(gwork_need, (size_t)fl.gstride * fl.count * (S / fl.ts));
             if (fl.smem > 200 * 1024) throw std::runtime_error("front too large for shared memory");
             fplan.push_back(fl);
             i = j;
@@ -231,7 +254,8 @@ void MfSolver::plan(int S) {
         for (int i = sl.begin; i < sl.begin + sl.count; ++i) {
             int f = sym.depth_fronts[i];
             int nf = sym.f_nf[f], k = sym.f_k[f];
-            size_t usz = (size_t)k * (nf + 1) - (size_t)k * (k - 1) / 2;
+            int kb = std::min(k, 32);      // largest staged block: the first (longest) kb rows
+            size_t usz = (size_t)kb * (nf + 1) - (size_t)kb * (kb - 1) / 2;
             smem = std::max(smem, (usz + nf) * sizeof(double));
             sl.max_nf = std::max(sl.max_nf, nf);
             sl.max_k = std::max(sl.max_k, k);
@@ -242,6 +266,7 @@ void MfSolver::plan(int S) {
     }
     d_U.alloc((size_t)sym.u_size * S);
     d_upd.alloc((size_t)sym.upd_size * S);
+    if (gwork_need) d_gwork.alloc(gwork_need);
     planned_S = S;
 }
 
@@ -262,11 +287,12 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
     for (const FactorLaunch& fl : fplan) {
         dim3 grid(fl.count, S / fl.ts);
         mf_factor_kernel<<<grid, fl.threads, fl.smem, st>>>(dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
-                                                            d_upd.p, S, fl.ts, fl.tr, active, status);
+                                                            d_upd.p, S, fl.ts, fl.tr, active, status,
+                                                            fl.global_front ? d_gwork.p : nullptr, fl.gstride);
     }
     for (const SolveLaunch& sl : splan) {
         if (S == 1) {
-            mf_backsolve_single<<<sl.count, 64, sl.smem, st>>>(dev, d_depth_fronts.p + sl.begin, d_U.p, x, active);
+            mf_backsolve_single<<<sl.count, 128, sl.smem, st>>>(dev, d_depth_fronts.p + sl.begin, d_U.p, x, active);
         } else {
             long long work = (long long)sl.count * S;
             int blocks = (int)((work + 127) / 128);

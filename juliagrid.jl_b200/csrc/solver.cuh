@@ -22,6 +22,8 @@ struct FactorLaunch {
     int threads;
     int tr;                // row lanes (power of two), column lanes = threads / ts / tr
     size_t smem;
+    bool global_front;     // front kept in a global workspace instead of shared memory
+    long long gstride;
 };
 
 struct SolveLaunch {
@@ -50,7 +52,7 @@ class MfSolver {
     DevBuf<int> d_f_k, d_f_nf, d_f_rowptr, d_f_rows, d_f_relptr, d_f_rel, d_f_childptr, d_f_children, d_f_asmptr,
         d_asm_src, d_asm_dst, d_level_fronts, d_depth_fronts;
     DevBuf<long long> d_f_uoff, d_f_updoff;
-    DevBuf<double> d_U, d_upd;
+    DevBuf<double> d_U, d_upd, d_gwork;
     DevSym dev{};
 };
 

@@ -1,0 +1,58 @@
+"""N-1 contingency batch (config 4 in small) through jgb_nr_batch vs per-scenario solves and the oracle."""
+import numpy as np
+import pytest
+
+import jgb200
+import oracle
+from oracle import nr as onr
+from conftest import oracle_system, product_system
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("case,count", [("case30test", 20), ("synthetic20", 70)])
+def test_outage_batch_matches_sequential(case, count, ctx):
+    ps = product_system(case)
+    a = jgb200.newton_raphson(ps, ctx)
+    elig = jgb200.eligible_outages(ps)[:count]
+    res = jgb200.nr_batch(a, elig)
+    assert (res.status == 0).all()
+    os_ = oracle_system(case)
+    for pos in (0, len(elig) // 2, len(elig) - 1):
+        k = int(elig[pos])
+        o_sys = os_.copy()
+        o_sys.status[k] = 0
+        o = onr.newton_raphson(o_sys)
+        assert onr.power_flow(o)
+        assert res.iterations[pos] == o.iteration
+        np.testing.assert_allclose(res.vm[pos], o.vm, atol=1e-8, rtol=0)
+        np.testing.assert_allclose(res.va[pos], o.va, atol=1e-8, rtol=0)
+    # and the in-place single-case route gives the same numbers as the batch
+    k = int(elig[1])
+    jgb200.update_branch(a, k, 0)
+    jgb200.set_initial_point(a)
+    assert jgb200.power_flow(a)
+    np.testing.assert_allclose(res.vm[1], a.voltage.magnitude, atol=1e-12)
+    assert res.iterations[1] == a.method.iteration
+    assert res.total_iterations == int(res.iterations.sum())
+
+
+def test_islanding_outage_is_reported_not_fatal(ctx):
+    """A bridge outage makes J singular for that scenario only: status -3 there, the rest of the batch converges."""
+    ps = product_system("case14test")
+    a = jgb200.newton_raphson(ps, ctx)
+    ks = np.array([0, 13, 3])          # branch 13 (7-15) is a bridge
+    res = jgb200.nr_batch(a, ks)
+    assert res.status[1] != 0
+    assert res.status[0] == 0 and res.status[2] == 0
+    assert 13 not in jgb200.eligible_outages(ps)
+
+
+def test_base_case_scenario_equals_power_flow(ctx):
+    ps = product_system("case30test")
+    a = jgb200.newton_raphson(ps, ctx)
+    res = jgb200.nr_batch(a, np.array([-1, -1, -1]))
+    assert jgb200.power_flow(a)
+    for s in range(3):
+        np.testing.assert_allclose(res.vm[s], a.voltage.magnitude, atol=1e-13)
+        assert res.iterations[s] == a.method.iteration == 4
