@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""Benchmark of the jgb200 hot path (contract in the round prompt, tier section ④).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--scenarios S]
+
+Workload (config.workload): the synthetic 10k-bus meshed grid of BASELINE.json configs[1], solved
+as the N-1 contingency sweep of configs[3]: every rank takes S independent branch-outage scenarios (weak scaling: S per
+GPU is fixed), runs full Newton-Raphson power flows (mismatch!/solve! to 1e-8) for all of them in one batch, and the
+ranks all-gather the converged states once. One step = one such batch; metric = Newton iterations (solve! calls) per
+second, whole job.  Extra keys report the single-case rates of configs[1] (NR) and configs[2] (GN-WLS).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "newton_iterations_per_s"
+UNIT = "NR iterations/s"
+TOL = 1e-8
+MAX_ITER = 20
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nm, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nm)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def result(self):
+        self.stop_flag.set()
+        self.join(timeout=3)
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------------------------- CPU reference arm
+def _cpu_worker(args):
+    """One process = one core: NR power flows for a slice of outage scenarios with the CPU restatement."""
+    ks, deadline = args
+    import oracle
+    from oracle import nr as onr
+    from oracle.fast import FastNR
+    from oracle.model import apply_outage
+    s = oracle.synthetic_grid()
+    base = oracle.ac_model(s)
+    a = onr.newton_raphson(s, base)
+    f = FastNR(a, FastNR.NOPIVOT)
+    iters = scen = 0
+    t0 = time.perf_counter()
+    for k in ks:
+        m = apply_outage(s, base, int(k))
+        f.set_y(m.nzval, m.nzval_t)
+        f.reset()
+        f.power_flow(MAX_ITER, TOL)
+        iters += f.iteration
+        scen += 1
+        if time.perf_counter() - t0 > deadline:
+            break
+    return iters, scen, time.perf_counter() - t0
+
+
+def cpu_rate(ks, cores, seconds):
+    """NR iterations/s of the CPU restatement (C assembly loops + SuperLU, no-pivot symmetric settings = the faster
+    of the two BASELINE.md §3 settings) on `cores` processes, bounded to about `seconds` of wall time."""
+    import multiprocessing as mp
+    chunks = [ks[i::cores] for i in range(cores)]
+    t0 = time.perf_counter()
+    if cores == 1:
+        res = [_cpu_worker((chunks[0], seconds))]
+    else:
+        with mp.get_context("spawn").Pool(cores) as pool:
+            res = pool.map(_cpu_worker, [(c, seconds) for c in chunks])
+    wall = time.perf_counter() - t0
+    iters = sum(r[0] for r in res)
+    scen = sum(r[1] for r in res)
+    busy = max(r[2] for r in res)
+    return iters / busy, iters, scen, busy, wall
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import jgb200
+    ps = jgb200.synthetic_grid()
+    elig = jgb200.eligible_outages(ps)
+    cores = os.cpu_count() or 1
+    per_step = max(cores, 2 * cores)           # bounded sample: 2 scenarios per core per step
+    t_all, iters_all, scen_all = [], 0, 0
+    for step in range(args.warmup + args.steps):
+        ks = elig[(step * per_step) % 4096: (step * per_step) % 4096 + per_step]
+        rate, iters, scen, busy, wall = cpu_rate(ks, cores, 60.0)
+        if step >= args.warmup:
+            t_all.append(wall)
+            iters_all += iters
+            scen_all += scen
+    total = sum(t_all)
+    value = iters_all / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(per_step, 1),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{scen_all} outage scenarios ({iters_all} NR iterations) of the same sweep, "
+                                   f"{cores} processes; CPU restatement of JuliaGrid (C loops + SuperLU no-pivot "
+                                   f"instead of UMFPACK/KLU) — Julia is not installed in this image"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def workload_config(S, world):
+    return {"workload": "synthetic 10k-bus meshed grid (seed 20261017, BASELINE configs[1]) Newton-Raphson AC power "
+                        "flow, N-1 contingency sweep (configs[3]): independent branch-outage solves to 1e-8 from the "
+                        "flat start, batched per GPU",
+            "buses": 10000, "branches": 12699, "dim_jacobian": 18498, "nnz_jacobian": 122308,
+            "scenarios_per_gpu": S, "scenarios_total": S * world, "tolerance": TOL, "max_iterations": MAX_ITER,
+            "l2_policy": "per-step working set (~4.5 MB x scenarios) is far larger than the 126 MB L2; no flush needed",
+            "parallelism": f"scenario-sharded x{world}, one all-gather of converged states"}
+
+
+# --------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import jgb200
+    from jgb200._lib import ptr
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    S = args.scenarios
+    stream = torch.cuda.current_stream().cuda_stream
+    ctx = jgb200.Context(local, stream)
+    lib = ctx.lib
+
+    ps = jgb200.synthetic_grid()
+    a = jgb200.newton_raphson(ps, ctx)
+    assert jgb200.power_flow(a) and a.method.iteration == 6, "base case must converge in 6 iterations"
+    jgb200.set_initial_point(a)
+    a._push_state()
+    elig = jgb200.eligible_outages(ps)
+    n = ps.n
+
+    def scenarios(step):
+        lo = ((step * world + rank) * S) % (len(elig) - S)
+        return elig[lo: lo + S]
+
+    # ---- buffers: pinned host + device
+    of_h = torch.empty(S, dtype=torch.int64).pin_memory()
+    ot_h = torch.empty(S, dtype=torch.int64).pin_memory()
+    dy_h = torch.empty((S, 8), dtype=torch.float64).pin_memory()
+    vm_h = torch.empty((S, n), dtype=torch.float64).pin_memory()
+    va_h = torch.empty((S, n), dtype=torch.float64).pin_memory()
+    it_h = torch.empty(S, dtype=torch.int32).pin_memory()
+    st_h = torch.empty(S, dtype=torch.int8).pin_memory()
+    of_d, ot_d, dy_d = of_h.to(dev), ot_h.to(dev), dy_h.to(dev)
+    vm_d = torch.empty((S, n), dtype=torch.float64, device=dev)
+    va_d = torch.empty((S, n), dtype=torch.float64, device=dev)
+    it_d = torch.empty(S, dtype=torch.int32, device=dev)
+    st_d = torch.empty(S, dtype=torch.int8, device=dev)
+    tot = C.c_int64(0)
+
+    def load(step, to_device):
+        of, ot, dy = jgb200.outage_arrays(ps, scenarios(step))
+        of_h.numpy()[:] = of
+        ot_h.numpy()[:] = ot
+        dy_h.numpy()[:] = dy
+        if to_device:
+            of_d.copy_(of_h)
+            ot_d.copy_(ot_h)
+            dy_d.copy_(dy_h)
+
+    def step_device():
+        ctx.check(lib.jgb_nr_batch_dev(ctx.handle, S, C.c_void_p(of_d.data_ptr()), C.c_void_p(ot_d.data_ptr()),
+                                       C.c_void_p(dy_d.data_ptr()), MAX_ITER, TOL, C.c_void_p(vm_d.data_ptr()),
+                                       C.c_void_p(va_d.data_ptr()), C.c_void_p(it_d.data_ptr()),
+                                       C.c_void_p(st_d.data_ptr()), C.byref(tot)))
+        if world > 1:
+            jgb200.dist.gather_batch_result(vm_d, va_d, it_d, st_d, total_rows=S * world)
+        return tot.value
+
+    def step_host():
+        ctx.check(lib.jgb_nr_batch(ctx.handle, S, C.cast(of_h.data_ptr(), C.POINTER(C.c_int64)),
+                                   C.cast(ot_h.data_ptr(), C.POINTER(C.c_int64)),
+                                   C.cast(dy_h.data_ptr(), C.POINTER(C.c_double)), MAX_ITER, TOL,
+                                   C.cast(vm_h.data_ptr(), C.POINTER(C.c_double)),
+                                   C.cast(va_h.data_ptr(), C.POINTER(C.c_double)),
+                                   C.cast(it_h.data_ptr(), C.POINTER(C.c_int32)),
+                                   C.cast(st_h.data_ptr(), C.POINTER(C.c_int8)), C.byref(tot)))
+        return tot.value
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, to_device, profile=False):
+        """W warm-up steps, then exactly K timed steps between CUDA events; max over ranks."""
+        for w in range(args.warmup):
+            load(w, to_device)
+            fn()
+        if profile:
+            torch.cuda.synchronize()
+            lib.jgb_profile(ctx.handle, 1)       # phase timers (CUDA events on the same stream) cover the timed region only
+        loads = []
+        iters = 0
+        launches0 = ctx.stat("launches")
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_host = 0.0
+        e0.record()
+        w0 = time.perf_counter()
+        for k in range(args.steps):
+            th = time.perf_counter()
+            load(args.warmup + k, to_device)       # device leg: staging the next batch is outside the metric...
+            t_host += time.perf_counter() - th
+            iters += fn()
+        e1.record()
+        barrier()
+        wall = time.perf_counter() - w0
+        ms = e0.elapsed_time(e1)
+        if to_device:
+            ms -= 1e3 * t_host                     # ...so its host time is removed from the device-resident figure
+        t = torch.tensor([ms, float(iters)], dtype=torch.float64, device=dev)
+        if world > 1:
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            tsum = t.clone()
+            dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+            ms, iters = float(tmax[0]), float(tsum[1])
+        return ms, iters, ctx.stat("launches") - launches0, wall
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ms_dev, iters_dev, launches, _ = timed(step_device, True, profile=True)
+    t_fac, t_bs, t_asm = ctx.stat("nr.time.factor_ms"), ctx.stat("nr.time.backsolve_ms"), ctx.stat("nr.time.assemble_ms")
+    n_fac = ctx.stat("nr.time.factor_count")
+    lib.jgb_profile(ctx.handle, 0)
+    ms_e2e, iters_e2e, _, _ = timed(step_host, False)
+    clocks = sampler.result() if rank == 0 else None
+    assert bool((st_h.numpy() == 0).all()), "every scenario of the sweep must converge"
+
+    # ---- single-case rates (configs[1] and [2]), rank 0 only, a few repetitions each
+    single = {}
+    if rank == 0:
+        reps = 5
+        jgb200.set_initial_point(a)
+        a._push_state()
+        jgb200.power_flow(a)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        it_sum = 0
+        for _ in range(reps):
+            jgb200.set_initial_point(a)
+            a._push_state()
+            jgb200.power_flow(a)
+            it_sum += a.method.iteration
+        torch.cuda.synchronize()
+        single["nr_single_case_iterations_per_s"] = it_sum / (time.perf_counter() - t0)
+        single["nr_single_case_iterations"] = a.method.iteration
+        try:
+            pw = jgb200.power(ps, a.voltage.magnitude, a.voltage.angle)
+            mon = jgb200.measurement(ps)
+            jgb200.add_voltmeter(mon, a.voltage.magnitude)
+            jgb200.add_wattmeter(mon, pw)
+            jgb200.add_varmeter(mon, pw)
+            buses = np.sort(np.random.default_rng(7).choice(n, n // 10, replace=False))
+            jgb200.add_pmu(mon, pw, a.voltage.magnitude, a.voltage.angle, buses=buses, polar=False)
+            se = jgb200.gauss_newton(mon, ctx)
+            t = se.method.tables
+            wd = np.ones(t.m)
+            cp = t.w_colptr - 1
+            for c in range(t.m):
+                wd[c] = t.w_nzval[cp[c]]
+            z = t.mean + np.sqrt(1 / wd) * np.random.default_rng(1).standard_normal(t.m)
+            jgb200.set_mean(se, z)
+            jgb200.state_estimation(se)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            it_sum = 0
+            for _ in range(3):
+                jgb200.set_voltage_se(se, ps.vm, ps.va)
+                jgb200.state_estimation(se)
+                it_sum += se.method.iteration
+            torch.cuda.synchronize()
+            single["wls_single_case_gn_iterations_per_s"] = it_sum / (time.perf_counter() - t0)
+            single["wls_single_case_iterations"] = se.method.iteration
+            single["wls_rows"] = int(t.m)
+        except Exception as e:      # the WLS extras must never sink the headline line
+            single["wls_error"] = str(e)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family (mf_factor_kernel: front assembly + partial LU + forward solve)
+    hbm, which = peaks()
+    # algorithmic bytes of ONE factor phase for S scenarios: read J values + mismatch, write packed U rows, write and
+    # read back every update block: 8 * (nnzJ + dim + u_size + 2 * upd_size) per scenario
+    nnzj, dimj = ctx.stat("nr.nnz_j"), ctx.stat("nr.dim")
+    bytes_fac = 8.0 * (nnzj + dimj + ctx.stat("nr.u_size") + 2 * ctx.stat("nr.upd_size")) * S
+    fac_launches = ctx.stat("nr.factor_launches")
+    achieved = (bytes_fac * n_fac) / (t_fac * 1e-3) / 1e9 if t_fac > 0 else 0.0
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(tp):
+        with open(tp) as fh:
+            traffic = json.load(fh).get("mf_factor_kernel_dram_bytes_per_factor_phase")
+    roofline = {"bound": "hbm", "kernel": "mf_factor_kernel (all launches of one factor phase)", "achieved": achieved,
+                "peak": hbm, "peak_source": which, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
+                "algorithmic_bytes_per_phase": bytes_fac, "launches_per_phase": fac_launches,
+                "avg_phase_ms": t_fac / max(1.0, n_fac),
+                "share_of_step": {"factor": t_fac / ms_dev, "backsolve": t_bs / ms_dev, "assemble": t_asm / ms_dev}}
+
+    # ---- CPU baseline: bounded sample of the same sweep on one host core (the reference is single-threaded)
+    rate, it_cpu, sc_cpu, busy, _ = cpu_rate(elig[:64], 1, 15.0)
+    cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"first {sc_cpu} outage scenarios of the sweep ({it_cpu} NR iterations, {busy:.1f} s) on 1 core; "
+                     "CPU restatement of JuliaGrid: C assembly loops + SciPy SuperLU (MMD_AT_PLUS_A, no pivoting) "
+                     "standing in for UMFPACK/KLU"}
+
+    value = iters_dev / (ms_dev * 1e-3)
+    e2e_v = iters_e2e / (ms_e2e * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(S, world),
+        "e2e": {"value": e2e_v, "unit": UNIT, "ms_per_step": ms_e2e / args.steps,
+                "h2d_bytes_per_step": int(S * (8 + 8 + 64)) * world, "d2h_bytes_per_step": int(S * (16 * n + 5)) * world},
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
+        "iterations_per_step": iters_dev / args.steps, **single,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--scenarios", type=int, default=1024, help="outage scenarios per GPU per step")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

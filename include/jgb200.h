@@ -127,6 +127,9 @@ int32_t jgb_wls_batch_dev(jgb_ctx* ctx, int64_t S, const double* Z_dev, int64_t 
  *      "nr.assemble_bytes" (per scenario-iteration), "nr.solve_bytes", "wls.*" likewise; kernel launch counter
  *      "launches" (since context creation).  Unknown key -> -1. */
 double jgb_stat(jgb_ctx* ctx, const char* key);
+/* enable / disable + reset the CUDA-event phase timers of the batch loops ("nr.time.assemble_ms", "nr.time.factor_ms",
+ * "nr.time.backsolve_ms", "wls.time.*"; accumulated since the last jgb_profile call) */
+int32_t jgb_profile(jgb_ctx* ctx, int32_t enable);
 
 /* ---- symbolic self-check (host only, no GPU work): runs the analysis on a CSC pattern and a host replay of the
  *      multifrontal schedule; used by the CPU test-suite to validate the maps the kernels consume. */

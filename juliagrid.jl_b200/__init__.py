@@ -12,3 +12,4 @@ from .measurement import (Measurement, measurement, power, add_voltmeter, add_am
 from .ac_state_estimation import (AcStateEstimation, gauss_newton, increment, solve_se, state_estimation,  # noqa: F401
                                   set_mean, set_voltage_se, gaussNewton, stateEstimation)
 from .batch import BatchResult, eligible_outages, outage_arrays, nr_batch, wls_batch  # noqa: F401
+from . import dist  # noqa: F401

@@ -44,6 +44,7 @@ PROTOTYPES = {
     "jgb_nr_batch_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]),
     "jgb_stat": (C.c_double, [C.c_void_p, C.c_char_p]),
+    "jgb_profile": (C.c_int32, [C.c_void_p, C.c_int32]),
     "jgb_selfcheck_symbolic": (C.c_int32, [C.c_int64, c_i64p, c_i64p, c_f64p, c_i64p, c_f64p, c_f64p, c_f64p]),
 }
 

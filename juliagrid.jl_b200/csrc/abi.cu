@@ -315,6 +315,16 @@ int32_t jgb_wls_batch_dev(jgb_ctx* ctx, int64_t S, const double* Z, int64_t max_
 }
 #endif  // JGB_WITH_WLS
 
+int32_t jgb_profile(jgb_ctx* ctx, int32_t enable) {
+    return guarded(ctx, [&] {
+        if (ctx->nr) { ctx->nr->timer.enabled = enable != 0; ctx->nr->timer.reset(); }
+#ifdef JGB_WITH_WLS
+        if (ctx->wls) { ctx->wls->timer.enabled = enable != 0; ctx->wls->timer.reset(); }
+#endif
+        return 0;
+    });
+}
+
 double jgb_stat(jgb_ctx* ctx, const char* key) {
     if (!ctx || !key) return -1.0;
     try {

@@ -79,4 +79,50 @@ struct PinnedBuf {
 
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 
+// CUDA-event phase timer on the context's stream (enabled by jgb_profile): marks are recorded while the work is
+// enqueued and resolved after the next stream synchronisation; accumulates milliseconds per phase name.
+struct PhaseTimer {
+    bool enabled = false;
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    struct Span { int phase; size_t a, b; };
+    std::vector<Span> spans;
+    double ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long count[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    ~PhaseTimer() { for (auto e : pool) cudaEventDestroy(e); }
+    cudaEvent_t mark(cudaStream_t st) {
+        if (!enabled) return nullptr;
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            JGB_CUDA(cudaEventCreate(&e));
+            pool.push_back(e);
+        }
+        cudaEvent_t e = pool[used++];
+        JGB_CUDA(cudaEventRecord(e, st));
+        return e;
+    }
+    cudaEvent_t reserve() {     // an event some other code records
+        if (!enabled) return nullptr;
+        if (used == pool.size()) {
+            cudaEvent_t e;
+            JGB_CUDA(cudaEventCreate(&e));
+            pool.push_back(e);
+        }
+        return pool[used++];
+    }
+    size_t last() const { return used - 1; }
+    void span(int phase, size_t a, size_t b) { if (enabled) spans.push_back({phase, a, b}); }
+    void resolve() {            // call after the stream has been synchronised
+        if (!enabled) return;
+        for (auto& sp : spans) {
+            float t = 0;
+            if (cudaEventElapsedTime(&t, pool[sp.a], pool[sp.b]) == cudaSuccess) { ms[sp.phase] += t; count[sp.phase]++; }
+        }
+        spans.clear();
+        used = 0;
+    }
+    void reset() { for (int i = 0; i < 8; ++i) { ms[i] = 0; count[i] = 0; } spans.clear(); used = 0; }
+};
+enum Phase { kPhAssemble = 0, kPhFactor = 1, kPhBacksolve = 2, kPhUpdate = 3, kPhGain = 4, kPhRows = 5 };
+
 }  // namespace jgb

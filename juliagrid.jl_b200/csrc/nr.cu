@@ -488,14 +488,27 @@ int NrContext::batch(int64_t Sreal64, const int64_t* of, const int64_t* ot, cons
     NrDev d = view(S, true);
     for (int64_t it = 0; it <= max_iter; ++it) {
         JGB_CUDA(cudaMemsetAsync(d_remaining.p, 0, sizeof(int), stream));
+        timer.mark(stream);
+        size_t e0 = timer.last();
         launch_assemble(S, true);
+        timer.mark(stream);
+        timer.span(kPhAssemble, e0, timer.last());
         nr_check_kernel<<<ceil_div(S, 128), 128, 0, stream>>>(d, S, Sreal, tol, (int)max_iter);
         ++launches;
         JGB_CUDA(cudaMemcpyAsync(h_int.p, d_remaining.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         JGB_CUDA(cudaStreamSynchronize(stream));
+        timer.resolve();
         if (h_int.p[0] == 0) break;
-        solver.factor_solve(b_jval.p, b_f.p, b_inc.p, S, b_active.p, b_status.p, stream);
+        timer.mark(stream);
+        size_t f0 = timer.last();
+        cudaEvent_t mid = timer.reserve();
+        size_t f1 = timer.last();
+        solver.factor_solve(b_jval.p, b_f.p, b_inc.p, S, b_active.p, b_status.p, stream, mid);
         launches += solver.launches_per_solve(S);
+        timer.mark(stream);
+        size_t f2 = timer.last();
+        timer.span(kPhFactor, f0, f1);
+        timer.span(kPhBacksolve, f1, f2);
         nr_update_kernel<<<(int)((ns + 127) / 128), 128, 0, stream>>>(d, S);
         ++launches;
     }
@@ -539,6 +552,14 @@ int NrContext::batch(int64_t Sreal64, const int64_t* of, const int64_t* ot, cons
 
 double NrContext::stat(const std::string& key) {
     const Symbolic& s = solver.sym;
+    if (key == "nr.time.assemble_ms") return timer.ms[kPhAssemble];
+    if (key == "nr.time.factor_ms") return timer.ms[kPhFactor];
+    if (key == "nr.time.backsolve_ms") return timer.ms[kPhBacksolve];
+    if (key == "nr.time.assemble_count") return (double)timer.count[kPhAssemble];
+    if (key == "nr.time.factor_count") return (double)timer.count[kPhFactor];
+    if (key == "nr.factor_launches") return solver.factor_launches(32);
+    if (key == "nr.u_size") return (double)s.u_size;
+    if (key == "nr.upd_size") return (double)s.upd_size;
     if (key == "nr.nnz_lu") return (double)s.nnz_lu;
     if (key == "nr.fronts") return s.nfronts;
     if (key == "nr.levels") return s.nlevels;

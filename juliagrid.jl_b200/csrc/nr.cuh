@@ -58,6 +58,7 @@ class NrContext {
     int n = 0, slack = -1, dim = 0, nnzj = 0, nnzy = 0;
     std::vector<int64_t> pq1, pvpq1, pcount1, jcolptr1, jrowval1;
     long long launches = 0;
+    PhaseTimer timer;
 
   private:
     void alloc_state(int S);

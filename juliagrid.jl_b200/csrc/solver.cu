@@ -282,7 +282,7 @@ int64_t MfSolver::factor_bytes(int S) const {
 }
 
 void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, int S, const unsigned char* active,
-                            int* status, cudaStream_t st) {
+                            int* status, cudaStream_t st, cudaEvent_t after_factor) {
     plan(S);
     for (const FactorLaunch& fl : fplan) {
         dim3 grid(fl.count, S / fl.ts);
@@ -290,6 +290,7 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
                                                             d_upd.p, S, fl.ts, fl.tr, active, status,
                                                             fl.global_front ? d_gwork.p : nullptr, fl.gstride);
     }
+    if (after_factor) JGB_CUDA(cudaEventRecord(after_factor, st));
     for (const SolveLaunch& sl : splan) {
         if (S == 1) {
             mf_backsolve_single<<<sl.count, 128, sl.smem, st>>>(dev, d_depth_fronts.p + sl.begin, d_U.p, x, active);

@@ -40,9 +40,10 @@ class MfSolver {
     // Factor A (values `aval`, CSC order of the analysed pattern, [nnz][S]) and solve A x = rhs for every scenario.
     // `active` (nullable, [S]) skips scenarios whose flag is 0. `status[s]` is set to -3 on a zero / non-finite pivot.
     void factor_solve(const double* aval, const double* rhs, double* x, int S, const unsigned char* active,
-                      int* status, cudaStream_t st);
+                      int* status, cudaStream_t st, cudaEvent_t after_factor = nullptr);
     int64_t factor_bytes(int S) const;     // algorithmic HBM bytes of one factor_solve (for roofline reports)
     int launches_per_solve(int S);
+    int factor_launches(int S) { plan(S); return (int)fplan.size(); }
 
   private:
     void plan(int S);

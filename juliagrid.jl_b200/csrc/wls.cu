@@ -693,6 +693,8 @@ WlsDev WlsContext::view(bool batch) {
 // normalEquation! + objective: rows kernel, then the two-stage objective reduction
 void WlsContext::launch_rows(int S, bool batch) {
     WlsDev d = view(batch);
+    timer.mark(stream);
+    const size_t t0 = timer.last();
     const long long work = (long long)m * S;
     wls_rows_kernel<<<(int)((work + kRowBlock - 1) / kRowBlock), kRowBlock, 0, stream>>>(d, S);
     if (S == 1) {
@@ -702,6 +704,8 @@ void WlsContext::launch_rows(int S, bool batch) {
     }
     wls_objective_final_kernel<<<ceil_div(S, 128), 128, 0, stream>>>(d, S, nrowblocks);
     launches += 3;
+    timer.mark(stream);
+    timer.span(kPhRows, t0, timer.last());
     JGB_CUDA(cudaGetLastError());
 }
 
@@ -709,11 +713,22 @@ void WlsContext::launch_rows(int S, bool batch) {
 void WlsContext::launch_gain(int S, bool batch) {
     WlsDev d = view(batch);
     const long long gw = (long long)nlow * S, rw = (long long)2 * n * S;
+    timer.mark(stream);
+    const size_t g0 = timer.last();
     wls_gain_kernel<<<(int)((gw + 127) / 128), 128, 0, stream>>>(d, S);
     wls_rhs_kernel<<<(int)((rw + 127) / 128), 128, 0, stream>>>(d, S);
     launches += 2;
-    solver.factor_solve(d.gval, d.rhs, d.inc, S, batch ? d.active : nullptr, d.status, stream);
+    timer.mark(stream);
+    const size_t g1 = timer.last();
+    cudaEvent_t mid = timer.reserve();
+    const size_t g2 = timer.last();
+    solver.factor_solve(d.gval, d.rhs, d.inc, S, batch ? d.active : nullptr, d.status, stream, mid);
     launches += solver.launches_per_solve(S);
+    timer.mark(stream);
+    const size_t g3 = timer.last();
+    timer.span(kPhGain, g0, g1);
+    timer.span(kPhFactor, g1, g2);
+    timer.span(kPhBacksolve, g2, g3);
     if (S == 1) wls_maxinc_kernel<<<dim3(ceil_div(2 * n, 512), 1), dim3(1, 128), 0, stream>>>(d, 1, 512);
     else wls_maxinc_kernel<<<dim3(ceil_div(2 * n, 128), S / 32), dim3(32, 4), 0, stream>>>(d, S, 128);
     ++launches;
@@ -734,6 +749,7 @@ void WlsContext::increment(double* max_inc, double* objective) {
     d_obj.download(h_d.p + 1, 1, stream);
     JGB_CUDA(cudaMemcpyAsync(h_i.p, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
     JGB_CUDA(cudaStreamSynchronize(stream));
+    timer.resolve();
     if (h_i.p[0] == -3) throw std::domain_error("singular gain matrix: zero or non-finite pivot");
     if (max_inc) *max_inc = h_d.p[0];
     if (objective) *objective = h_d.p[1];
@@ -780,6 +796,7 @@ int WlsContext::run(int64_t max_iter, double tol, int64_t* iters, double* max_in
         d_maxinc.download(h_d.p, 1, stream);
         d_obj.download(h_d.p + 1, 1, stream);
         JGB_CUDA(cudaStreamSynchronize(stream));
+        timer.resolve();
         if (h_i.p[0] == 0) { rc = h_i.p[1]; break; }
         wls_update_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(d, 1);
         ++launches;
@@ -836,6 +853,7 @@ int WlsContext::batch(int64_t Sreal64, const double* Z, bool dev_in, int64_t max
         ++launches;
         JGB_CUDA(cudaMemcpyAsync(h_i.p, d_remaining.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         JGB_CUDA(cudaStreamSynchronize(stream));
+        timer.resolve();
         if (h_i.p[0] == 0) break;
         wls_update_kernel<<<(int)((ns + 127) / 128), 128, 0, stream>>>(d, S);
         ++launches;
@@ -881,6 +899,13 @@ int WlsContext::batch(int64_t Sreal64, const double* Z, bool dev_in, int64_t max
 
 double WlsContext::stat(const std::string& key) {
     const Symbolic& s = solver.sym;
+    if (key == "wls.time.rows_ms") return timer.ms[kPhRows];
+    if (key == "wls.time.gain_ms") return timer.ms[kPhGain];
+    if (key == "wls.time.factor_ms") return timer.ms[kPhFactor];
+    if (key == "wls.time.backsolve_ms") return timer.ms[kPhBacksolve];
+    if (key == "wls.time.factor_count") return (double)timer.count[kPhFactor];
+    if (key == "wls.u_size") return (double)s.u_size;
+    if (key == "wls.upd_size") return (double)s.upd_size;
     if (key == "wls.nnz_lu") return (double)s.nnz_lu;
     if (key == "wls.fronts") return s.nfronts;
     if (key == "wls.levels") return s.nlevels;

@@ -79,6 +79,7 @@ class WlsContext {
     std::vector<int64_t> gcolptr1, growval1;
     long long launches = 0;
     long long nterms = 0;
+    PhaseTimer timer;
 
   private:
     WlsDev view(bool batch);

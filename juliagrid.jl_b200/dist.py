@@ -1,0 +1,60 @@
+"""Scenario sharding across GPUs (one process per GPU) and the single all-gather of converged states.
+
+The reference has no distributed code; contingencies / Monte-Carlo draws are independent user-loop iterations
+(SURVEY.md §3.4-3.5). Every rank runs the same deterministic setup (no broadcast), solves its contiguous block of
+scenarios, and one all-gather over NCCL (NVLink/NVSwitch) — gloo on CPU in the tests — assembles the global result.
+`torch.distributed` is plumbing only: no collective sits on the numerical path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(total: int, rank: int, world: int):
+    """Contiguous block [lo, hi) of `total` scenarios owned by `rank`; sizes differ by at most one."""
+    base, extra = divmod(total, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def shard(items, rank: int, world: int):
+    lo, hi = shard_bounds(len(items), rank, world)
+    return items[lo:hi]
+
+
+def allgather_rows(local, total_rows: int | None = None, group=None):
+    """All-gather row blocks of a 2-D (or 1-D) tensor whose per-rank row counts follow shard_bounds().
+    `local` is a torch tensor (CUDA for NCCL, CPU for gloo). Returns the concatenation in rank order."""
+    import torch
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if total_rows is None:
+        counts = [torch.zeros(1, dtype=torch.int64, device=local.device) for _ in range(world)]
+        dist.all_gather(counts, torch.tensor([local.shape[0]], dtype=torch.int64, device=local.device), group=group)
+        sizes = [int(c.item()) for c in counts]
+    else:
+        sizes = [shard_bounds(total_rows, r, world)[1] - shard_bounds(total_rows, r, world)[0] for r in range(world)]
+    assert sizes[rank] == local.shape[0]
+    if len(set(sizes)) == 1:
+        out = torch.empty((world * sizes[0],) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+        return out
+    pad = max(sizes)
+    buf = torch.zeros((pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    buf[: local.shape[0]] = local
+    out = torch.empty((world * pad,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    return torch.cat([out[r * pad: r * pad + sizes[r]] for r in range(world)], dim=0)
+
+
+def gather_batch_result(vm, va, iterations, status, total_rows=None, group=None):
+    """The one collective of the sweep: converged states [Vm | Va] (FP64), iteration counts and status bytes."""
+    import torch
+    state = allgather_rows(torch.cat([vm, va], dim=1), total_rows, group)
+    n = vm.shape[1]
+    meta = allgather_rows(torch.stack([iterations.to(torch.int32), status.to(torch.int32)], dim=1), total_rows, group)
+    return state[:, :n], state[:, n:], meta[:, 0], meta[:, 1]

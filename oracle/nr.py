@@ -219,10 +219,10 @@ def fill_jacobian(a: NewtonRaphson):
                     cur_t += V[q] * (Gk * s - Bk * c)               # PiQiSumMinus
                     if is_pq:
                         cur_v += V[q] * (Gk * c + Bk * s)           # PiQiSumPlus
-                nz[pa] = V[row] * (-cur_t) - B * V[row] ** 2        # Piθi (:105)
+                nz[pa] = V[row] * (-cur_t) - B * (V[row] * V[row])        # Piθi (:105)
                 pa += 1
                 if is_pq:
-                    nz[qa] = V[row] * cur_v - G * V[row] ** 2       # Qiθi (:130)
+                    nz[qa] = V[row] * cur_v - G * (V[row] * V[row])       # Qiθi (:130)
                     qa += 1
                     nz[pm] = cur_v + G * V[row]                     # PiVi (:113)
                     pm += 1

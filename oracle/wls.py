@@ -357,12 +357,12 @@ def normal_equation(a: GaussNewton):
             if code == 6:
                 a.residual[row] = a.mean[row] - V[i] * cs_plus
                 obj(row)
-                H[pos(row, i)] = V[i] * (-cs_minus) - Bii * V[i] ** 2        # Piθi
+                H[pos(row, i)] = V[i] * (-cs_minus) - Bii * (V[i] * V[i])        # Piθi
                 H[pos(row, i + n)] = cs_plus + Gii * V[i]                    # PiVi
             else:
                 a.residual[row] = a.mean[row] - V[i] * cs_minus
                 obj(row)
-                H[pos(row, i)] = V[i] * cs_plus - Gii * V[i] ** 2            # Qiθi
+                H[pos(row, i)] = V[i] * cs_plus - Gii * (V[i] * V[i])            # Qiθi
                 H[pos(row, i + n)] = cs_minus - Bii * V[i]                   # QiVi
             for q in range(mdl.colptr[i], mdl.colptr[i + 1]):
                 j = int(mdl.rowval[q])
@@ -401,54 +401,54 @@ def normal_equation(a: GaussNewton):
         d = T[i] - T[j] - phi                            # ViVjθijState (equations.jl:20-30)
         s, c = sin(d), cos(d)
         if code == 7:       # Pij (equations.jl:147-176)
-            A, B_, C = tinv ** 2 * (g + gsi), tinv * g, tinv * b
-            h = A * Vi ** 2 - (B_ * c + C * s) * Vi * Vj
+            A, B_, C = (tinv * tinv) * (g + gsi), tinv * g, tinv * b
+            h = A * (Vi * Vi) - (B_ * c + C * s) * Vi * Vj
             dti = (B_ * s - C * c) * Vi * Vj
             dvi = 2 * A * Vi - (B_ * c + C * s) * Vj
             dtj = -dti
             dvj = -(B_ * c + C * s) * Vi
         elif code == 8:     # Pji (:183-212)
             A, B_, C = g + gsi, tinv * g, tinv * b
-            h = A * Vj ** 2 - (B_ * c - C * s) * Vi * Vj
+            h = A * (Vj * Vj) - (B_ * c - C * s) * Vi * Vj
             dti = (B_ * s + C * c) * Vi * Vj
             dvi = (-B_ * c + C * s) * Vj
             dtj = -dti
             dvj = 2 * A * Vj - (B_ * c - C * s) * Vi
         elif code == 10:    # Qij (:215-244)
-            A, B_, C = tinv ** 2 * (b + bsi), tinv * g, tinv * b
-            h = -A * Vi ** 2 - (B_ * s - C * c) * Vi * Vj
+            A, B_, C = (tinv * tinv) * (b + bsi), tinv * g, tinv * b
+            h = -A * (Vi * Vi) - (B_ * s - C * c) * Vi * Vj
             dti = -(B_ * c + C * s) * Vi * Vj
             dvi = -2 * A * Vi - (B_ * s - C * c) * Vj
             dtj = -dti
             dvj = -(B_ * s - C * c) * Vi
         elif code == 11:    # Qji (:247-276)
             A, B_, C = b + bsi, tinv * g, tinv * b
-            h = -A * Vj ** 2 + (B_ * s + C * c) * Vi * Vj
+            h = -A * (Vj * Vj) + (B_ * s + C * c) * Vi * Vj
             dti = (B_ * c - C * s) * Vi * Vj
             dvi = (B_ * s + C * c) * Vj
             dtj = -dti
             dvj = -2 * A * Vj + (B_ * s + C * c) * Vi
         elif code in (2, 4, 14):   # Iij family (:279-331, 389-423)
             A = tinv ** 4 * ((g + gsi) ** 2 + (b + bsi) ** 2)
-            B_ = tinv ** 2 * (g ** 2 + b ** 2)
+            B_ = (tinv * tinv) * (g ** 2 + b ** 2)
             C = tinv ** 3 * (g * (g + gsi) + b * (b + bsi))
             D = tinv ** 3 * (g * bsi - b * gsi)
             if code == 2:
-                iinv = 1 / (sqrt(A * Vi ** 2 + B_ * Vj ** 2 - 2 * Vi * Vj * (C * c - D * s)))
+                iinv = 1 / (sqrt(A * (Vi * Vi) + B_ * (Vj * Vj) - 2 * Vi * Vj * (C * c - D * s)))
                 h = 1 / iinv
                 dti = iinv * (C * s + D * c) * Vi * Vj
                 dvi = iinv * (A * Vi - (C * c - D * s) * Vj)
                 dtj = -dti
                 dvj = iinv * (B_ * Vj - (C * c - D * s) * Vi)
             elif code == 4:
-                h = A * Vi ** 2 + B_ * Vj ** 2 - 2 * Vi * Vj * (C * c - D * s)
+                h = A * (Vi * Vi) + B_ * (Vj * Vj) - 2 * Vi * Vj * (C * c - D * s)
                 dti = 2 * (C * s + D * c) * Vi * Vj
                 dvi = 2 * (A * Vi - (C * c - D * s) * Vj)
                 dtj = -dti
                 dvj = 2 * (B_ * Vj - (C * c - D * s) * Vi)
             else:
                 # ψij: phasor from ψijCoefficient + ViVjθiθjState (:389-407), derivatives with Iij coefficients
-                pA, pB = tinv ** 2 * (g + gsi), tinv ** 2 * (b + bsi)
+                pA, pB = (tinv * tinv) * (g + gsi), (tinv * tinv) * (b + bsi)
                 pC, pD = tinv * g, tinv * b
                 si, ci = sin(T[i]), cos(T[i])
                 sj, cj = sin(T[j] + phi), cos(T[j] + phi)
@@ -456,24 +456,24 @@ def normal_equation(a: GaussNewton):
                 im = (pA * si + pB * ci) * Vi - (pC * sj + pD * cj) * Vj
                 iinv2 = 1 / (re * re + im * im)
                 h = atan2(im, re)
-                dti = iinv2 * (A * Vi ** 2 - (C * c - D * s) * Vi * Vj)
+                dti = iinv2 * (A * (Vi * Vi) - (C * c - D * s) * Vi * Vj)
                 dvi = -iinv2 * (C * s + D * c) * Vj
-                dtj = iinv2 * (B_ * Vj ** 2 - (C * c - D * s) * Vi * Vj)
+                dtj = iinv2 * (B_ * (Vj * Vj) - (C * c - D * s) * Vi * Vj)
                 dvj = iinv2 * (C * s + D * c) * Vi
         elif code in (3, 5, 15):   # Iji family (:334-386, 426-458)
-            A = tinv ** 2 * (g ** 2 + b ** 2)
+            A = (tinv * tinv) * (g ** 2 + b ** 2)
             B_ = (g + gsi) ** 2 + (b + bsi) ** 2
             C = tinv * (g * (g + gsi) + b * (b + bsi))
             D = tinv * (g * bsi - gsi * b)
             if code == 3:
-                iinv = 1 / sqrt(A * Vi ** 2 + B_ * Vj ** 2 - 2 * Vi * Vj * (C * c + D * s))
+                iinv = 1 / sqrt(A * (Vi * Vi) + B_ * (Vj * Vj) - 2 * Vi * Vj * (C * c + D * s))
                 h = 1 / iinv
                 dti = iinv * (C * s - D * c) * Vi * Vj
                 dvi = iinv * (A * Vi - (C * c + D * s) * Vj)
                 dtj = -dti
                 dvj = iinv * (B_ * Vj - (C * c + D * s) * Vi)
             elif code == 5:
-                h = A * Vi ** 2 + B_ * Vj ** 2 - 2 * Vi * Vj * (C * c + D * s)
+                h = A * (Vi * Vi) + B_ * (Vj * Vj) - 2 * Vi * Vj * (C * c + D * s)
                 dti = 2 * (C * s - D * c) * Vi * Vj
                 dvi = 2 * (A * Vi - (C * c + D * s) * Vj)
                 dtj = -dti
@@ -487,12 +487,12 @@ def normal_equation(a: GaussNewton):
                 im = (pA * sj + pB * cj) * Vj - (pC * si + pD * ci) * Vi
                 iinv2 = 1 / (re * re + im * im)
                 h = atan2(im, re)
-                dti = iinv2 * (A * Vi ** 2 - (C * c + D * s) * Vi * Vj)
+                dti = iinv2 * (A * (Vi * Vi) - (C * c + D * s) * Vi * Vj)
                 dvi = -iinv2 * (C * s - D * c) * Vj
-                dtj = iinv2 * (B_ * Vj ** 2 - (C * c + D * s) * Vi * Vj)
+                dtj = iinv2 * (B_ * (Vj * Vj) - (C * c + D * s) * Vi * Vj)
                 dvj = iinv2 * (C * s - D * c) * Vi
         elif code in (18, 20):     # Re/Im Iij (:466-505)
-            pA, pB = tinv ** 2 * (g + gsi), tinv ** 2 * (b + bsi)
+            pA, pB = (tinv * tinv) * (g + gsi), (tinv * tinv) * (b + bsi)
             pC, pD = tinv * g, tinv * b
             si, ci = sin(T[i]), cos(T[i])
             sj, cj = sin(T[j] + phi), cos(T[j] + phi)

@@ -1,0 +1,173 @@
+"""CPU-only checks: the C-ABI library loads and exports every symbol of include/jgb200.h, host logic of the product
+against the oracle, the symbolic analysis through its host replay, the C oracle against the NumPy oracle, and that
+the product fails loudly without a GPU (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+import scipy.sparse.linalg as spla
+
+import jgb200
+import oracle
+from oracle import nr as onr, wls as owls, post
+from jgb200._lib import ptr
+from conftest import ROOT, oracle_system, product_system
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "jgb200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(jgb_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_header_symbol():
+    lib = jgb200.load()
+    syms = header_symbols()
+    assert len(syms) >= 30
+    for name in syms:
+        assert hasattr(lib, name), f"{name} declared in include/jgb200.h but not exported"
+    assert sorted(jgb200.exported_symbols()) == syms, "ctypes prototypes and header disagree"
+    assert lib.jgb_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device jgb_create must fail with -5 (skipped on the GPU box)."""
+    lib = jgb200.load()
+    rc = C.c_int32(0)
+    h = lib.jgb_create(0, None, C.byref(rc))
+    if h:
+        lib.jgb_destroy(h)
+        pytest.skip("a GPU is present")
+    assert rc.value == -5
+    assert b"no CPU fallback" in lib.jgb_last_error(None)
+    with pytest.raises(jgb200.JgbError):
+        jgb200.Context(0)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "juliagrid.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".jl")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+@pytest.mark.parametrize("case", ["case14test", "case30test", "synthetic20", "case_ACTIVSg10k"])
+def test_product_model_matches_oracle(case):
+    ps, os_ = product_system(case), oracle_system(case)
+    m, om = jgb200.ac_model(ps), oracle.ac_model(os_)
+    assert np.array_equal(m.colptr - 1, om.colptr) and np.array_equal(m.rowval - 1, om.rowval)
+    scale = np.abs(om.nzval).max()
+    np.testing.assert_allclose(m.nzval, om.nzval, rtol=0, atol=4e-16 * scale)
+    np.testing.assert_allclose(m.nzval_t, om.nzval_t, rtol=0, atol=4e-16 * scale)
+    from jgb200.ac_power_flow import _initialize
+    bt, sl, vm, va = _initialize(ps)
+    obt, osl, ovm, ova = onr.initialize(os_)
+    assert np.array_equal(bt, obt) and sl == osl and np.array_equal(vm, ovm) and np.array_equal(va, ova)
+
+
+def test_synthetic_grid_recipes_agree():
+    a, b = jgb200.synthetic_grid(side=30), oracle.synthetic_grid(side=30)
+    for k in ("pd", "qd", "frm", "to", "r", "x", "b", "tap", "bus_type", "gen_bus", "gen_p", "gen_vm"):
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+@pytest.mark.parametrize("case", ["case14test", "case30test", "synthetic20", "synthetic10k"])
+def test_symbolic_host_replay_solves_jacobian(case):
+    """jgb_selfcheck_symbolic: ordering + fronts + assembly maps replayed on the host solve J x = f like SuperLU."""
+    o = onr.newton_raphson(oracle_system(case))
+    onr.mismatch(o)
+    onr.fill_jacobian(o)
+    n = o.dim
+    grp = np.zeros(n, dtype=np.int64)
+    for i in range(o.mdl.n):
+        if o.pvpq[i] >= 0:
+            grp[o.pvpq[i]] = i
+        if o.pq[i] >= 0:
+            grp[o.pq[i]] = i
+    cp, rv = (o.j_colptr + 1).astype(np.int64), (o.j_rowval + 1).astype(np.int64)
+    x, stats = np.zeros(n), np.zeros(8)
+    rc = jgb200.load().jgb_selfcheck_symbolic(n, ptr(cp, C.c_int64), ptr(rv, C.c_int64), ptr(o.j_nzval, C.c_double),
+                                              ptr(grp, C.c_int64), ptr(o.mismatch, C.c_double), ptr(x, C.c_double),
+                                              ptr(stats, C.c_double))
+    assert rc == 0
+    J = onr.jacobian_csc(o)
+    ref = spla.splu(J).solve(o.mismatch)
+    assert np.abs(J @ x - o.mismatch).max() <= 1e-10 * max(1.0, np.abs(o.mismatch).max())
+    np.testing.assert_allclose(x, ref, rtol=1e-7, atol=1e-10 * max(1.0, np.abs(ref).max()))
+    assert stats[0] >= 1 and stats[1] >= 1 and stats[3] >= len(rv)
+
+
+def test_symbolic_rejects_bad_input():
+    lib = jgb200.load()
+    assert lib.jgb_selfcheck_symbolic(0, None, None, None, None, None, None, None) == -1
+    cp, rv = np.array([1, 2, 3], dtype=np.int64), np.array([1, 9], dtype=np.int64)
+    assert lib.jgb_selfcheck_symbolic(2, ptr(cp, C.c_int64), ptr(rv, C.c_int64), None, None, None, None, None) == -4
+
+
+@pytest.mark.parametrize("case", ["case14test", "synthetic20", "case_ACTIVSg10k"])
+def test_c_oracle_matches_numpy_oracle(case):
+    from oracle.fast import FastNR
+    a = onr.newton_raphson(oracle_system(case))
+    f = FastNR(a)
+    assert f.mismatch() == onr.mismatch(a)
+    f.jacobian()
+    onr.fill_jacobian(a)
+    assert np.array_equal(f.mism, a.mismatch) and np.array_equal(f.jnz, a.j_nzval)
+    if case != "case_ACTIVSg10k":
+        assert f.power_flow() and onr.power_flow(a)
+        assert f.iteration == a.iteration
+        np.testing.assert_allclose(f.vm, a.vm, atol=1e-12)
+
+
+def test_wls_tables_match_oracle():
+    """Product acWLS tables (H pattern, W, mean, type, index, range) == oracle's, every device class and flag."""
+    ps, os_ = product_system("case14test"), oracle_system("case14test")
+    ps.model = jgb200.ac_model(ps)
+    o = onr.newton_raphson(os_)
+    assert onr.power_flow(o)
+    pw = jgb200.power(ps, o.vm, o.va)
+    pw_o = post.powers(os_, o.mdl, o.vm, o.va)
+    for k in pw:
+        np.testing.assert_allclose(pw[k], pw_o[k], atol=1e-13)
+    mon = jgb200.measurement(ps)
+    jgb200.add_voltmeter(mon, o.vm)
+    jgb200.add_ammeter(mon, pw)
+    jgb200.add_ammeter(mon, pw, square=True)
+    jgb200.add_wattmeter(mon, pw)
+    jgb200.add_varmeter(mon, pw)
+    for kw in (dict(polar=True), dict(polar=True, square=True), dict(polar=False), dict(polar=False, correlated=True)):
+        jgb200.add_pmu(mon, pw, o.vm, o.va, buses=range(ps.n), branch=True, **kw)
+    mon.watt["status"][5] = 0
+    mon.pmu["mag_status"][3] = 0
+    mon.pmu["ang_status"][40] = 0
+    t = jgb200.ac_wls(ps, mon)
+    g = owls.gauss_newton(os_, mon, o.mdl)
+    ex = owls.export_one_based(g)
+    assert t.m == g.m
+    for k in ("h_colptr", "h_rowval", "type", "index", "range"):
+        assert np.array_equal(getattr(t, k), ex[k]), k
+    assert np.array_equal(t.mean, g.mean)
+    assert np.array_equal(t.w_colptr - 1, g.w.indptr) and np.array_equal(t.w_rowval - 1, g.w.indices)
+    np.testing.assert_allclose(t.w_nzval, g.w.data, rtol=1e-15)
+
+
+def test_eligible_outages_counts():
+    """12 567 non-islanding outages on the synthetic grid, 8 729 on ACTIVSg10k."""
+    assert len(jgb200.eligible_outages(product_system("synthetic10k"))) == 12567
+    assert len(jgb200.eligible_outages(product_system("case_ACTIVSg10k"))) == 8729
+    assert 13 not in jgb200.eligible_outages(product_system("case14test"))
+
+
+def test_shard_bounds_cover_everything():
+    for total in (0, 1, 7, 10000, 12567):
+        for world in (1, 2, 3, 8):
+            pieces = [jgb200.dist.shard_bounds(total, r, world) for r in range(world)]
+            assert pieces[0][0] == 0 and pieces[-1][1] == total
+            assert all(pieces[i][1] == pieces[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in pieces]
+            assert max(sizes) - min(sizes) <= 1
