@@ -1,0 +1,197 @@
+# JuliaGridB200.jl — overlay package: the `B200` tag that routes JuliaGrid's Newton-Raphson power flow and
+# Gauss-Newton WLS state estimation to libjgb200.so (hand-written sm_100a CUDA kernels) through `ccall`.
+#
+# Host code only. It reads the reference's own structures (`PowerSystem`, `Measurement`, the tables `acWLS` builds)
+# and passes their arrays — Float64 / Int64 (1-based) / Int8 / ComplexF64 — straight to the C ABI of include/jgb200.h.
+# NOTE: Julia is not installed in the build image, so this file has been reviewed by eye only; the same ABI is
+# exercised by the Python host mirror (juliagrid.jl_b200/*.py) in the test-suite.
+module JuliaGridB200
+
+using JuliaGrid
+import JuliaGrid: newtonRaphson, gaussNewton, mismatch!, solve!, increment!, powerFlow!, stateEstimation!,
+    setInitialPoint!, AC, Polar, PowerSystem, Measurement, Normal
+
+const libjgb = get(ENV, "JGB200_LIB", joinpath(@__DIR__, "..", "libjgb200.so"))
+
+"Factorisation tag: `newtonRaphson(system, B200)`, `gaussNewton(monitoring, B200)`."
+struct B200 <: Normal end
+
+mutable struct Ctx
+    handle::Ptr{Cvoid}
+    function Ctx(device::Integer = 0, stream::Ptr{Cvoid} = C_NULL)
+        rc = Ref{Int32}(0)
+        h = ccall((:jgb_create, libjgb), Ptr{Cvoid}, (Int32, Ptr{Cvoid}, Ref{Int32}), device, stream, rc)
+        h == C_NULL && throw(ErrorException(unsafe_string(ccall((:jgb_last_error, libjgb), Cstring, (Ptr{Cvoid},), C_NULL))))
+        ctx = new(h)
+        finalizer(c -> ccall((:jgb_destroy, libjgb), Cvoid, (Ptr{Cvoid},), c.handle), ctx)
+        return ctx
+    end
+end
+
+function check(ctx::Ctx, rc::Int32)
+    rc < 0 && throw(ErrorException(unsafe_string(ccall((:jgb_last_error, libjgb), Cstring, (Ptr{Cvoid},), ctx.handle))))
+    return rc      # rc == 1: iteration cap reached — not an error, as in the reference (print/solver.jl:426-442)
+end
+
+##### Newton-Raphson #####
+mutable struct NewtonRaphsonB200
+    jacobianColptr::Vector{Int64}
+    jacobianRowval::Vector{Int64}
+    mismatch::Vector{Float64}
+    increment::Vector{Float64}
+    pq::Vector{Int64}
+    pvpq::Vector{Int64}
+    pcount::Vector{Int64}
+    iteration::Int64
+    ctx::Ctx
+end
+
+mutable struct AcPowerFlowB200 <: AC
+    voltage::Polar
+    power::JuliaGrid.AcPower
+    current::JuliaGrid.AcCurrent
+    method::NewtonRaphsonB200
+    system::PowerSystem
+end
+
+function newtonRaphson(system::PowerSystem, ::Type{B200}; device::Integer = 0)
+    ref = newtonRaphson(system, LU)                   # reference constructor: bus-type fix-ups, start point, acModel!
+    ac = system.model.ac
+    bus = system.bus
+    ctx = Ctx(device)
+    Y, Yt = ac.nodalMatrix, ac.nodalMatrixTranspose
+    GC.@preserve Y Yt begin
+        check(ctx, ccall((:jgb_nr_setup, libjgb), Int32,
+            (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Int8}, Int64),
+            ctx.handle, bus.number, Y.colptr, Y.rowval, pointer(reinterpret(Float64, Y.nzval)),
+            pointer(reinterpret(Float64, Yt.nzval)), bus.layout.type, bus.layout.slack))
+    end
+    dim, nnzJ = Ref{Int64}(0), Ref{Int64}(0)
+    check(ctx, ccall((:jgb_nr_dims, libjgb), Int32, (Ptr{Cvoid}, Ref{Int64}, Ref{Int64}), ctx.handle, dim, nnzJ))
+    m = NewtonRaphsonB200(zeros(Int64, dim[] + 1), zeros(Int64, nnzJ[]), zeros(dim[]), zeros(dim[]),
+        zeros(Int64, bus.number), zeros(Int64, bus.number), zeros(Int64, bus.number), 0, ctx)
+    check(ctx, ccall((:jgb_nr_pattern, libjgb), Int32,
+        (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}, Ptr{Int64}),
+        ctx.handle, m.pq, m.pvpq, m.pcount, m.jacobianColptr, m.jacobianRowval))
+    check(ctx, ccall((:jgb_nr_set_injection, libjgb), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        ctx.handle, bus.supply.active, bus.supply.reactive, bus.demand.active, bus.demand.reactive))
+    analysis = AcPowerFlowB200(ref.voltage, ref.power, ref.current, m, system)
+    pushState!(analysis)
+    return analysis
+end
+
+pushState!(a::AcPowerFlowB200) = check(a.method.ctx, ccall((:jgb_nr_set_state, libjgb), Int32,
+    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
+pullState!(a::AcPowerFlowB200) = check(a.method.ctx, ccall((:jgb_nr_get_state, libjgb), Int32,
+    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
+
+function mismatch!(a::AcPowerFlowB200)
+    sp, sq = Ref{Float64}(0), Ref{Float64}(0)
+    check(a.method.ctx, ccall((:jgb_nr_mismatch, libjgb), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}),
+        a.method.ctx.handle, sp, sq))
+    return sp[], sq[]
+end
+
+function solve!(a::AcPowerFlowB200)
+    check(a.method.ctx, ccall((:jgb_nr_solve, libjgb), Int32, (Ptr{Cvoid},), a.method.ctx.handle))
+    a.method.iteration += 1
+    pullState!(a)
+    return nothing
+end
+
+function powerFlow!(a::AcPowerFlowB200; iteration::Int64 = 20, tolerance::Float64 = 1e-8,
+    power::Bool = false, current::Bool = false, verbose::Int64 = 0)
+    pushState!(a)
+    it, sp, sq = Ref{Int64}(0), Ref{Float64}(0), Ref{Float64}(0)
+    check(a.method.ctx, ccall((:jgb_nr_run, libjgb), Int32,
+        (Ptr{Cvoid}, Int64, Float64, Ref{Int64}, Ref{Float64}, Ref{Float64}),
+        a.method.ctx.handle, iteration, tolerance, it, sp, sq))
+    a.method.iteration = it[]
+    pullState!(a)
+    power && JuliaGrid.power!(a)        # generic `AC` post-processing of the reference keeps working
+    current && JuliaGrid.current!(a)
+    return nothing
+end
+
+##### Gauss-Newton WLS #####
+mutable struct GaussNewtonB200
+    mean::Vector{Float64}
+    residual::Vector{Float64}
+    increment::Vector{Float64}
+    type::Vector{Int8}
+    index::Vector{Int64}
+    range::Vector{Int64}
+    objective::Float64
+    iteration::Int64
+    ctx::Ctx
+end
+
+mutable struct AcStateEstimationB200 <: AC
+    voltage::Polar
+    power::JuliaGrid.AcPower
+    current::JuliaGrid.AcCurrent
+    method::GaussNewtonB200
+    system::PowerSystem
+    monitoring::Measurement
+end
+
+function gaussNewton(monitoring::Measurement, ::Type{B200}; device::Integer = 0)
+    system = monitoring.system
+    jcb, mean, pcs, rsd, type, index, range, power, current, _ = JuliaGrid.acWLS(system, monitoring)
+    ac, bus, br = system.model.ac, system.bus, system.branch
+    ctx = Ctx(device)
+    Y, Yt = ac.nodalMatrix, ac.nodalMatrixTranspose
+    GC.@preserve Y Yt jcb pcs begin
+        check(ctx, ccall((:jgb_wls_setup, libjgb), Int32,
+            (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Int8}, Ptr{Int64}, Ptr{Int64},
+             Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64},
+             Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            ctx.handle, bus.number, length(mean), bus.layout.slack, jcb.colptr, jcb.rowval, type, index, range,
+            pcs.colptr, pcs.rowval, pcs.nzval, Y.colptr, Y.rowval, pointer(reinterpret(Float64, Y.nzval)),
+            pointer(reinterpret(Float64, Yt.nzval)), br.number, br.layout.from, br.layout.to,
+            br.parameter.conductance, br.parameter.susceptance, br.parameter.turnsRatio, br.parameter.shiftAngle,
+            pointer(reinterpret(Float64, ac.admittance))))
+    end
+    check(ctx, ccall((:jgb_wls_set_mean, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.handle, mean))
+    m = GaussNewtonB200(mean, rsd, zeros(2 * bus.number), type, index, range, 0.0, 0, ctx)
+    a = AcStateEstimationB200(Polar(copy(bus.voltage.magnitude), copy(bus.voltage.angle)), power, current, m,
+        system, monitoring)
+    check(ctx, ccall((:jgb_wls_set_state, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+        ctx.handle, a.voltage.magnitude, a.voltage.angle))
+    return a
+end
+
+function increment!(a::AcStateEstimationB200)
+    mi, ob = Ref{Float64}(0), Ref{Float64}(0)
+    check(a.method.ctx, ccall((:jgb_wls_increment, libjgb), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}),
+        a.method.ctx.handle, mi, ob))
+    a.method.objective = ob[]
+    return mi[]
+end
+
+function solve!(a::AcStateEstimationB200)
+    check(a.method.ctx, ccall((:jgb_wls_solve, libjgb), Int32, (Ptr{Cvoid},), a.method.ctx.handle))
+    a.method.iteration += 1
+    check(a.method.ctx, ccall((:jgb_wls_get_state, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+        a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
+    return nothing
+end
+
+function stateEstimation!(a::AcStateEstimationB200; iteration::Int64 = 40, tolerance::Float64 = 1e-8,
+    power::Bool = false, current::Bool = false, verbose::Int64 = 0)
+    it, mi, ob = Ref{Int64}(0), Ref{Float64}(0), Ref{Float64}(0)
+    check(a.method.ctx, ccall((:jgb_wls_run, libjgb), Int32,
+        (Ptr{Cvoid}, Int64, Float64, Ref{Int64}, Ref{Float64}, Ref{Float64}),
+        a.method.ctx.handle, iteration, tolerance, it, mi, ob))
+    a.method.iteration, a.method.objective = it[], ob[]
+    check(a.method.ctx, ccall((:jgb_wls_get_state, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+        a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
+    power && JuliaGrid.power!(a)
+    current && JuliaGrid.current!(a)
+    return nothing
+end
+
+export B200
+
+end # module
