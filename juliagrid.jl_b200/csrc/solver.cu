@@ -7,6 +7,8 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
+#include <string>
 
 namespace jgb {
 
@@ -18,17 +20,20 @@ __device__ __forceinline__ long long urow_off(int p, int nf) {
 
 // One CTA = one front x TS scenarios. Thread t: scenario lane sl = t % TS, entry lane e = t / TS,
 // entry lanes are arranged TR (rows) x TC (columns). Front F is column major, ld = nf, nf+1 columns,
-// element (r,c) of scenario lane sl at F[(r + c*nf) * TS + sl].
+// element (r,c) of scenario lane sl at F[(r + c*nf) * TS + sl].  TS and the address space of F are compile-time
+// so that the front is addressed with LDS/STS and shifts (a runtime select would degrade to generic LD/ST).
+template <int TS, bool GLOBAL_F>
 __global__ void __launch_bounds__(256)
 mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ aval,
-                 const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S, int TS,
+                 const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S,
                  int TR, const unsigned char* __restrict__ active, int* __restrict__ status, double* gwork,
                  long long gstride) {
     extern __shared__ double Fs[];
-    // fronts too large for shared memory live in a per-CTA global (L2-resident) workspace
-    double* F = gwork ? gwork + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * gstride : Fs;
-    const int f = fronts[blockIdx.x];
     const int sl = threadIdx.x % TS;
+    double* Fl;     // this thread's scenario lane of the front: element (r,c) at Fl[(r + c*nf) * TS]
+    if constexpr (GLOBAL_F) Fl = gwork + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * gstride + sl;
+    else Fl = Fs + sl;
+    const int f = fronts[blockIdx.x];
     const int e0 = threadIdx.x / TS;
     const int TE = blockDim.x / TS;
     const int er = e0 % TR, ec = e0 / TR, TC = TE / TR;
@@ -40,38 +45,43 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __rest
     const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
     const int total = nf * (nf + 1);
 
-    for (int pos = e0; pos < total; pos += TE) F[pos * TS + sl] = 0.0;
+    for (int pos = e0; pos < total; pos += TE) Fl[pos * TS] = 0.0;
     __syncthreads();
     if (act) {
+        const double* __restrict__ av = aval + s;
         const int a1 = sy.f_asmptr[f + 1];
         for (int a = sy.f_asmptr[f] + e0; a < a1; a += TE)
-            F[sy.asm_dst[a] * TS + sl] = aval[(long long)sy.asm_src[a] * S + s];
-        for (int p = e0; p < k; p += TE) F[(p + nf * nf) * TS + sl] = rhs[(long long)rows[p] * S + s];
+            Fl[sy.asm_dst[a] * TS] = av[(long long)sy.asm_src[a] * S];
+        for (int p = e0; p < k; p += TE) Fl[(p + nf * nf) * TS] = rhs[(long long)rows[p] * S + s];
     }
     __syncthreads();
-    for (int ci = sy.f_childptr[f]; ci < sy.f_childptr[f + 1]; ++ci) {
-        const int c = sy.f_children[ci];
-        const int uc = sy.f_nf[c] - sy.f_k[c];
-        const int* __restrict__ rel = sy.f_rel + sy.f_relptr[c];
-        const double* __restrict__ C = upd + sy.f_updoff[c] * S + s;
-        if (act) {
-            for (int j = ec; j <= uc; j += TC) {
-                const int dc = (j < uc) ? rel[j] : nf;
-                for (int i = er; i < uc; i += TR)
-                    F[(rel[i] + dc * nf) * TS + sl] += C[(long long)(i + j * uc) * S];
-            }
+    // extend-add of all children as one gather: each destination sums its sources in child order (deterministic),
+    // destinations are distinct, so no barrier is needed between children
+    // update storage is tile major: element e of scenario s at [((s / W) * upd_size + e) * W + s % W], W = min(S, 32)
+    const int W = S < 32 ? S : 32;
+    double* __restrict__ up = upd + (long long)(s / W) * sy.upd_size * W + (s % W);
+    if (act) {
+        const int d1 = sy.f_eaptr[f + 1];
+        for (int d = sy.f_eaptr[f] + e0; d < d1; d += TE) {
+            const int dst = sy.ea_dst[d] * TS;
+            double acc = Fl[dst];
+            const int t1 = sy.ea_srcptr[d + 1];
+            for (int t = sy.ea_srcptr[d]; t < t1; ++t) acc += up[(long long)sy.ea_src[t] * W];
+            Fl[dst] = acc;
         }
-        __syncthreads();
     }
+    __syncthreads();
     bool bad = false;
+    const int colstride = nf * TS;
     for (int p = 0; p < k; ++p) {
-        const double piv = F[(p + p * nf) * TS + sl];
+        const double* colp = Fl + p * colstride;
+        const double piv = colp[p * TS];
         if (piv == 0.0 || !isfinite(piv)) bad = true;
         const double inv = 1.0 / piv;
         for (int j = p + 1 + ec; j <= nf; j += TC) {
-            const double m = inv * F[(p + j * nf) * TS + sl];
-            for (int i = p + 1 + er; i < nf; i += TR)
-                F[(i + j * nf) * TS + sl] -= F[(i + p * nf) * TS + sl] * m;
+            double* colj = Fl + j * colstride;
+            const double m = inv * colj[p * TS];
+            for (int i = p + 1 + er; i < nf; i += TR) colj[i * TS] -= colp[i * TS] * m;
         }
         __syncthreads();
     }
@@ -81,14 +91,231 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __rest
     for (int p = ec; p < k; p += TC) {
         double* Urow = Uf + urow_off(p, nf) * S;
         for (int j = p + er; j <= nf; j += TR) {
-            const double v = F[(p + j * nf) * TS + sl];
+            const double v = Fl[(p + j * nf) * TS];
             Urow[(long long)(j - p) * S] = (j == p) ? 1.0 / v : v;
         }
     }
-    double* __restrict__ Cf = upd + sy.f_updoff[f] * S + s;
-    for (int j = ec; j <= u; j += TC)
-        for (int i = er; i < u; i += TR)
-            Cf[(long long)(i + j * u) * S] = F[((k + i) + (k + j) * nf) * TS + sl];
+    double* __restrict__ Cf = up + sy.f_updoff[f] * W;
+    for (int j = ec; j <= u; j += TC) {
+        const double* colj = Fl + ((k + j) * nf + k) * TS;
+        double* Cj = Cf + (long long)j * u * W;
+        for (int i = er; i < u; i += TR) Cj[(long long)i * W] = colj[i * TS];
+    }
+}
+
+// ---- TMA-staged variant for the many small fronts of a batch -------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
+constexpr int kBulkMaxChildren = 32;   // children staged per group
+
+// One CTA = one front x one tile of 32 scenarios (lane = scenario), TE warps split the entries. The update blocks
+// of the children are contiguous runs in the tile-major update storage, so one elected thread fetches a whole group
+// of them with cp.async.bulk (TMA) into a staging area behind the front while the other threads zero the front and
+// assemble the matrix entries; completion is signalled through an mbarrier. All later traffic is coalesced
+// 256-byte lines. Shared memory: [front nf*(nf+1)*32 doubles][staging cap*32 doubles][rel list cap ints].
+template <int TE, int MAXNF>
+__global__ void __launch_bounds__(32 * TE)
+mf_factor_bulk_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ aval,
+                      const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S,
+                      int smem_elems, const unsigned char* __restrict__ active, int* __restrict__ status) {
+    extern __shared__ __align__(128) double sm[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ int s_off[kBulkMaxChildren], s_uc[kBulkMaxChildren], s_relo[kBulkMaxChildren], s_gend;
+    constexpr int TR = TE >= 4 ? 4 : TE, TC = TE / TR;
+    const int sl = threadIdx.x & 31, e0 = threadIdx.x >> 5;
+    const int er = e0 % TR, ec = e0 / TR;
+    const int f = fronts[blockIdx.x];
+    const int s = blockIdx.y * 32 + sl;
+    const bool act = active ? (active[s] != 0) : true;
+    if (!__syncthreads_or(act)) return;
+    const int nf = sy.f_nf[f], k = sy.f_k[f], u = nf - k;
+    const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
+    const int fsz = nf * (nf + 1);
+    double* Fl = sm + sl;
+    double* stage = sm + fsz * 32;
+    const int cap = smem_elems - fsz;
+    int* srel = reinterpret_cast<int*>(sm + (size_t)smem_elems * 32);
+    double* __restrict__ uptile = upd + (long long)blockIdx.y * sy.upd_size * 32;
+    const int c0 = sy.f_childptr[f], c1 = sy.f_childptr[f + 1];
+
+    if (threadIdx.x == 0 && c1 > c0) mbar_init(&mbar, 1);
+    for (int pos = e0; pos < fsz; pos += TE) Fl[pos * 32] = 0.0;
+    __syncthreads();
+    {
+        const double* __restrict__ av = aval + s;
+        const int a1 = sy.f_asmptr[f + 1];
+        for (int a = sy.f_asmptr[f] + e0; a < a1; a += TE) Fl[sy.asm_dst[a] * 32] = av[(long long)sy.asm_src[a] * S];
+        for (int p = e0; p < k; p += TE) Fl[(p + nf * nf) * 32] = rhs[(long long)rows[p] * S + s];
+    }
+    uint32_t parity = 0;
+    for (int ci = c0; ci < c1;) {
+        if (threadIdx.x == 0) {
+            int off = 0, ro = 0, g = 0, c2 = ci;
+            while (c2 < c1 && g < kBulkMaxChildren) {
+                const int c = sy.f_children[c2];
+                const int uc = sy.f_nf[c] - sy.f_k[c];
+                const int blk = uc * (uc + 1);
+                if (g > 0 && off + blk > cap) break;
+                s_off[g] = off; s_uc[g] = uc; s_relo[g] = ro;
+                off += blk; ro += uc; ++g; ++c2;
+            }
+            s_gend = c2;
+            mbar_expect_tx(&mbar, (uint32_t)off * 256u);
+            for (int q = 0; q < g; ++q) {
+                const int c = sy.f_children[ci + q];
+                bulk_g2s(stage + (size_t)s_off[q] * 32, uptile + sy.f_updoff[c] * 32, (uint32_t)(s_uc[q] * (s_uc[q] + 1)) * 256u,
+                         &mbar);
+            }
+        }
+        __syncthreads();
+        const int gend = s_gend;
+        // relative indices of the group's children into shared memory while the bulk copies are in flight
+        for (int q = ci + e0; q < gend; q += TE) {
+            const int c = sy.f_children[q];
+            const int* __restrict__ rel = sy.f_rel + sy.f_relptr[c];
+            const int uc = s_uc[q - ci];
+            for (int i = sl; i < uc; i += 32) srel[s_relo[q - ci] + i] = rel[i];
+        }
+        __syncthreads();
+        mbar_wait(&mbar, parity);
+        parity ^= 1;
+        for (int q = 0; q < gend - ci; ++q) {
+            const int uc = s_uc[q];
+            const int* r = srel + s_relo[q];
+            const double* st = stage + (size_t)s_off[q] * 32 + sl;
+            for (int j = ec; j <= uc; j += TC) {
+                const int dc = (j < uc) ? r[j] : nf;
+                double* colj = Fl + dc * nf * 32;
+                const double* sj = st + j * uc * 32;
+                for (int i = er; i < uc; i += TR) colj[r[i] * 32] += sj[i * 32];
+            }
+            __syncthreads();
+        }
+        ci = gend;
+    }
+    __syncthreads();
+    // ---- elimination in registers: warp e0 owns columns e0, e0 + TE, ... of the front (nf + 1 columns incl. rhs).
+    // Each pivot column is broadcast through a small double-buffered shared-memory strip; all loops are unrolled to
+    // the compile-time bound MAXNF so every register index is static, rows/columns beyond nf are predicated off.
+    constexpr int NC = (MAXNF + 1 + TE - 1) / TE;
+    double col[NC][MAXNF];
+    double* bc = stage;    // staging area is free now: 2 x MAXNF x 32 doubles
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+        const int c = e0 + q * TE;
+#pragma unroll
+        for (int i = 0; i < MAXNF; ++i) col[q][i] = (c <= nf && i < nf) ? Fl[(i + c * nf) * 32] : 0.0;
+    }
+    bool bad = false;
+    double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
+#pragma unroll
+    for (int p = 0; p < MAXNF; ++p) {
+        if (p >= k) break;
+        double* b = bc + (p & 1) * (MAXNF * 32) + sl;
+        if (e0 == p % TE) {
+#pragma unroll
+            for (int i = p; i < MAXNF; ++i)
+                if (i < nf) b[i * 32] = col[p / TE][i];
+        }
+        __syncthreads();
+        const double piv = b[p * 32];
+        if (piv == 0.0 || !isfinite(piv)) bad = true;
+        const double inv = 1.0 / piv;
+        double l[MAXNF];
+#pragma unroll
+        for (int i = p + 1; i < MAXNF; ++i) l[i] = (i < nf) ? b[i * 32] : 0.0;
+        double* Urow = Uf + urow_off(p, nf) * S;
+#pragma unroll
+        for (int q = 0; q < NC; ++q) {
+            const int c = e0 + q * TE;
+            if (c >= p && c <= nf) {
+                const double upc = col[q][p];                      // U[p, c]
+                if (act) Urow[(long long)(c - p) * S] = (c == p) ? inv : upc;
+                if (c > p) {
+                    const double m = inv * upc;
+#pragma unroll
+                    for (int i = p + 1; i < MAXNF; ++i) col[q][i] -= l[i] * m;
+                }
+            }
+        }
+    }
+    if (!act) return;
+    if (bad && e0 == 0) status[s] = -3;
+    double* __restrict__ Cf = uptile + sy.f_updoff[f] * 32 + sl;
+#pragma unroll
+    for (int q = 0; q < NC; ++q) {
+        const int c = e0 + q * TE;
+        if (c >= k && c <= nf) {
+            double* Cj = Cf + (long long)(c - k) * u * 32;
+#pragma unroll
+            for (int i = 0; i < MAXNF; ++i)
+                if (i >= k && i < nf) Cj[(i - k) * 32] = col[q][i];
+        }
+    }
+}
+
+template <bool GLOBAL_F>
+void launch_factor(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st, DevSym dev, const int* fronts,
+                   const double* aval, const double* rhs, double* U, double* upd, int S, int tr,
+                   const unsigned char* active, int* status, double* gwork, long long gstride) {
+#define JGB_CASE(T)                                                                                              \
+    case T:                                                                                                      \
+        mf_factor_kernel<T, GLOBAL_F><<<grid, threads, smem, st>>>(dev, fronts, aval, rhs, U, upd, S, tr, active, \
+                                                                   status, gwork, gstride);                      \
+        break;
+    switch (ts) {
+        JGB_CASE(1) JGB_CASE(2) JGB_CASE(4) JGB_CASE(8) JGB_CASE(16) JGB_CASE(32)
+        default: throw std::runtime_error("unsupported scenario tile");
+    }
+#undef JGB_CASE
+}
+
+// (lanes per scenario, register bound on the front order) variants of the bulk kernel
+#define JGB_BULK_VARIANTS(X) X(4, 8) X(4, 12) X(8, 16) X(8, 20)
+
+void launch_factor_bulk(int maxnf, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const int* fronts,
+                        const double* aval, const double* rhs, double* U, double* upd, int S, int smem_elems,
+                        const unsigned char* active, int* status) {
+#define X(TE, MAXNF)                                                                                              \
+    if (maxnf == MAXNF) {                                                                                         \
+        mf_factor_bulk_kernel<TE, MAXNF><<<grid, 32 * TE, smem, st>>>(dev, fronts, aval, rhs, U, upd, S, smem_elems, \
+                                                                      active, status);                           \
+        return;                                                                                                   \
+    }
+    JGB_BULK_VARIANTS(X)
+#undef X
+    throw std::runtime_error("unsupported bulk factor variant");
+}
+
+int bulk_variant_for(int nf) { return nf <= 8 ? 8 : nf <= 12 ? 12 : nf <= 16 ? 16 : nf <= 20 ? 20 : 0; }
+int bulk_lanes_for(int maxnf) { return maxnf <= 12 ? 4 : 8; }
+
+template <int TS>
+void set_factor_smem_attr() {
+    JGB_CUDA(cudaFuncSetAttribute(mf_factor_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
 // Backward substitution, S == 1: one CTA per front, pivots processed in blocks of 32 rows from the bottom up.
@@ -142,26 +369,58 @@ mf_backsolve_single(DevSym sy, const int* __restrict__ fronts, const double* __r
     for (int p = threadIdx.x; p < k; p += blockDim.x) x[rows[p]] = xs[p];
 }
 
-// Backward substitution, batch: one thread per (front, scenario); lanes of a warp are consecutive scenarios, so every
-// U / x access is a coalesced 256-byte line.
+// Backward substitution, batch: one CTA per (front, tile of TS scenarios), TE = blockDim / TS lanes per scenario.
+// The front's packed U rows and the already known x of its update rows are staged in shared memory with coalesced
+// loads; phase A removes the update-row part of every pivot row (rows distributed over the lanes, no reduction),
+// phase B solves the k x k triangle column by column with one barrier per pivot.
+template <int TS>
 __global__ void __launch_bounds__(128)
-mf_backsolve_batch(DevSym sy, const int* __restrict__ fronts, int nfr, const double* __restrict__ U,
-                   double* __restrict__ x, int S, const unsigned char* __restrict__ active) {
-    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int fi = (int)(gid / S);
-    const int s = (int)(gid % S);
-    if (fi >= nfr) return;
-    if (active && !active[s]) return;
-    const int f = fronts[fi];
+mf_backsolve_tile_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ U,
+                         double* __restrict__ x, int S, const unsigned char* __restrict__ active) {
+    extern __shared__ double sh[];
+    const int sl = threadIdx.x % TS, e = threadIdx.x / TS, TE = blockDim.x / TS;
+    const int s = blockIdx.y * TS + sl;
+    const bool act = active ? (active[s] != 0) : true;
+    if (!__syncthreads_or(act)) return;
+    const int f = fronts[blockIdx.x];
     const int nf = sy.f_nf[f], k = sy.f_k[f];
     const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
+    const int usz = (int)urow_off(k, nf);
+    double* xs = sh + sl;                 // xs[j * TS]
+    double* Us = sh + nf * TS + sl;       // Us[e * TS], packed rows
     const double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
-    for (int p = k - 1; p >= 0; --p) {
-        const double* Urow = Uf + urow_off(p, nf) * S;
-        double acc = Urow[(long long)(nf - p) * S];
-        for (int j = p + 1; j < nf; ++j) acc -= Urow[(long long)(j - p) * S] * x[(long long)rows[j] * S + s];
-        x[(long long)rows[p] * S + s] = acc * Urow[0];
+    for (int q = e; q < usz; q += TE) Us[q * TS] = Uf[(long long)q * S];
+    for (int j = k + e; j < nf; j += TE) xs[j * TS] = x[(long long)rows[j] * S + s];
+    __syncthreads();
+    for (int p = e; p < k; p += TE) {
+        const double* Urow = Us + (int)urow_off(p, nf) * TS;
+        double acc = Urow[(nf - p) * TS];
+        for (int j = k; j < nf; ++j) acc -= Urow[(j - p) * TS] * xs[j * TS];
+        xs[p * TS] = acc;
     }
+    __syncthreads();
+    for (int p = k - 1; p >= 0; --p) {
+        if (e == p % TE) xs[p * TS] *= Us[(int)urow_off(p, nf) * TS];
+        __syncthreads();
+        const double xp = xs[p * TS];
+        for (int q = e; q < p; q += TE) xs[q * TS] -= Us[((int)urow_off(q, nf) + (p - q)) * TS] * xp;
+    }
+    __syncthreads();
+    if (act)
+        for (int p = e; p < k; p += TE) x[(long long)rows[p] * S + s] = xs[p * TS];
+}
+
+void launch_backsolve_tile(int ts, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const int* fronts,
+                           const double* U, double* x, int S, const unsigned char* active) {
+#define JGB_CASE(T)                                                                                   \
+    case T:                                                                                           \
+        mf_backsolve_tile_kernel<T><<<grid, 128, smem, st>>>(dev, fronts, U, x, S, active);           \
+        break;
+    switch (ts) {
+        JGB_CASE(1) JGB_CASE(2) JGB_CASE(4) JGB_CASE(8) JGB_CASE(16) JGB_CASE(32)
+        default: throw std::runtime_error("unsupported scenario tile");
+    }
+#undef JGB_CASE
 }
 
 constexpr int kMaxSmemFront = 150;    // nf*(nf+1)*8 bytes must fit the 200 KB dynamic shared-memory budget
@@ -187,6 +446,10 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st) {
     d_f_asmptr.upload(sym.f_asmptr, st);
     d_asm_src.upload(sym.asm_src, st);
     d_asm_dst.upload(sym.asm_dst, st);
+    d_f_eaptr.upload(sym.f_eaptr, st);
+    d_ea_dst.upload(sym.ea_dst, st);
+    d_ea_srcptr.upload(sym.ea_srcptr, st);
+    d_ea_src.upload(sym.ea_src, st);
     d_level_fronts.upload(sym.level_fronts, st);
     d_depth_fronts.upload(sym.depth_fronts, st);
     std::vector<long long> uo(sym.f_uoff.begin(), sym.f_uoff.end()), po(sym.f_updoff.begin(), sym.f_updoff.end());
@@ -197,18 +460,60 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st) {
     dev.f_relptr = d_f_relptr.p; dev.f_rel = d_f_rel.p; dev.f_childptr = d_f_childptr.p;
     dev.f_children = d_f_children.p; dev.f_asmptr = d_f_asmptr.p; dev.asm_src = d_asm_src.p;
     dev.asm_dst = d_asm_dst.p; dev.f_uoff = d_f_uoff.p; dev.f_updoff = d_f_updoff.p;
+    dev.f_eaptr = d_f_eaptr.p; dev.ea_dst = d_ea_dst.p; dev.ea_srcptr = d_ea_srcptr.p; dev.ea_src = d_ea_src.p;
     planned_S = -1;
-    JGB_CUDA(cudaFuncSetAttribute(mf_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    set_factor_smem_attr<1>(); set_factor_smem_attr<2>(); set_factor_smem_attr<4>();
+    set_factor_smem_attr<8>(); set_factor_smem_attr<16>(); set_factor_smem_attr<32>();
+    JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+#define X(TE, MAXNF) \
+    JGB_CUDA(cudaFuncSetAttribute(mf_factor_bulk_kernel<TE, MAXNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JGB_BULK_VARIANTS(X)
+#undef X
+    dev.upd_size = sym.upd_size;
     JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 }
+
+namespace {
+struct PlanRule { int maxnf, ts, threads; };
+
+// "maxnf:ts:threads,..." (ascending maxnf); environment overrides are for tuning experiments only
+std::vector<PlanRule> parse_rules(const char* env, const std::vector<PlanRule>& dflt) {
+    const char* v = env ? getenv(env) : nullptr;
+    if (!v || !*v) return dflt;
+    std::vector<PlanRule> out;
+    std::string str(v);
+    size_t pos = 0;
+    while (pos < str.size()) {
+        size_t end = str.find(',', pos);
+        if (end == std::string::npos) end = str.size();
+        PlanRule r{0, 1, 32};
+        if (sscanf(str.substr(pos, end - pos).c_str(), "%d:%d:%d", &r.maxnf, &r.ts, &r.threads) >= 2) out.push_back(r);
+        pos = end + 1;
+    }
+    return out.empty() ? dflt : out;
+}
+}  // namespace
 
 void MfSolver::plan(int S) {
     if (S == planned_S) return;
     fplan.clear();
     splan.clear();
     size_t gwork_need = 0;
-    const int cls_bound[] = {6, 16, 48, kMaxSmemFront, 1 << 30};
-    auto cls = [&](int nf) { int c = 0; while (nf > cls_bound[c]) ++c; return c; };
+    // factor launch classes: fronts of a level are sorted by decreasing order and cut at these bounds
+    static const std::vector<PlanRule> single_rules = {{6, 1, 32}, {16, 1, 64}, {48, 1, 128}, {kMaxSmemFront, 1, 256}};
+    static const std::vector<PlanRule> batch_rules = {{8, 32, 128}, {12, 32, 128}, {16, 32, 256}, {20, 32, 256},
+                                                      {24, 8, 256}, {32, 8, 256}, {48, 4, 256}, {64, 2, 256},
+                                                      {96, 1, 256}, {kMaxSmemFront, 1, 256}};
+    const char* nb = getenv("JGB_NO_BULK");
+    const bool bulk_enabled = !(nb && *nb == '1');
+    const std::vector<PlanRule> rules = (S == 1) ? parse_rules("JGB_FPLAN_SINGLE", single_rules)
+                                                 : parse_rules("JGB_FPLAN_BATCH", batch_rules);
+    auto cls = [&](int nf) { size_t c = 0; while (c < rules.size() && nf > rules[c].maxnf) ++c; return (int)c; };
     for (int l = 0; l < sym.nlevels; ++l) {
         int b = sym.levelptr[l], e = sym.levelptr[l + 1];
         int i = b;
@@ -221,23 +526,45 @@ void MfSolver::plan(int S) {
             FactorLaunch fl{};
             fl.begin = i;
             fl.count = j - i;
-            fl.global_front = nf > kMaxSmemFront;
-            if (fl.global_front) {
+            fl.global_front = nf > kMaxSmemFront || c >= (int)rules.size();
+            fl.bulk = false;
+            if (!fl.global_front && S >= 32 && bulk_enabled && bulk_variant_for(nf) != 0) {
+                fl.maxnf = bulk_variant_for(nf);
+                // TMA-staged kernel: front + staging for the children's update blocks must fit in shared memory
+                int need = 0;
+                for (int q = i; q < j; ++q) {
+                    const int f = sym.level_fronts[q];
+                    const int fsz = sym.f_nf[f] * (sym.f_nf[f] + 1);
+                    int largest = 0, total_c = 0;
+                    for (int ci = sym.f_childptr[f]; ci < sym.f_childptr[f + 1]; ++ci) {
+                        const int cc = sym.f_children[ci];
+                        const int uc = sym.f_nf[cc] - sym.f_k[cc];
+                        largest = std::max(largest, uc * (uc + 1));
+                        total_c += uc * (uc + 1);
+                    }
+                    need = std::max(need, fsz + std::max(2 * fl.maxnf, std::min(total_c, std::max(largest, 192))));
+                }
+                size_t bytes = (size_t)need * 256 + (size_t)need * 4 + 64;
+                if (bytes <= 200 * 1024) {
+                    fl.bulk = true;
+                    fl.ts = 32;
+                    fl.smem_elems = need;
+                    fl.threads = 32 * bulk_lanes_for(fl.maxnf);
+                    fl.smem = bytes;
+                }
+            }
+            if (fl.bulk) {
+            } else if (fl.global_front) {
                 fl.ts = (S == 1) ? 1 : 4;
                 fl.threads = 256;
-            } else if (S == 1) {
-                fl.ts = 1;
-                fl.threads = nf <= 6 ? 32 : nf <= 16 ? 64 : nf <= 48 ? 128 : 256;
             } else {
-                int cap = (int)std::max<size_t>(1, (size_t)(160 * 1024) / per);
-                fl.ts = std::min(32, pow2_floor(cap));
-                int te = pow2_floor(std::max(1, std::min(256 / fl.ts, nf * (nf + 1) / 16)));
-                fl.threads = fl.ts * te;
-                if (fl.threads < 32) { fl.threads = 32; }
+                fl.ts = std::min(rules[c].ts, S);
+                fl.threads = std::max(rules[c].threads, fl.ts);
+                while (fl.ts > 1 && per * fl.ts > 200 * 1024) fl.ts /= 2;
             }
             int te = fl.threads / fl.ts;
-            fl.tr = std::min(te, 16);
-            fl.smem = fl.global_front ? 0 : per * fl.ts;
+            fl.tr = std::min(pow2_floor(te), 16);
+            if (!fl.bulk) fl.smem = fl.global_front ? 0 : per * fl.ts;
             fl.gstride = (long long)nf * (nf + 1) * fl.ts;
             if (fl.global_front)
                 gwork_need = std::max<size_t>(gwork_need, (size_t)fl.gstride * fl.count * (S / fl.ts));
@@ -246,23 +573,52 @@ void MfSolver::plan(int S) {
             i = j;
         }
     }
+    // back-solve: one launch per depth level; batch launches are additionally cut by front size so that the
+    // scenario tile (shared-memory footprint of the staged U rows) matches the class
+    static const std::vector<PlanRule> bs_rules = {{8, 32, 128}, {12, 32, 128}, {16, 32, 128}, {24, 16, 128},
+                                                   {32, 8, 128}, {48, 4, 128}, {64, 4, 128}, {96, 2, 128},
+                                                   {1 << 30, 1, 128}};
+    const std::vector<PlanRule> brules = parse_rules("JGB_BPLAN_BATCH", bs_rules);
+    auto bcls = [&](int nf) { size_t c = 0; while (c + 1 < brules.size() && nf > brules[c].maxnf) ++c; return (int)c; };
     for (int d = 0; d < sym.ndepths; ++d) {
-        SolveLaunch sl{};
-        sl.begin = sym.depthptr[d];
-        sl.count = sym.depthptr[d + 1] - sl.begin;
-        size_t smem = 0;
-        for (int i = sl.begin; i < sl.begin + sl.count; ++i) {
-            int f = sym.depth_fronts[i];
-            int nf = sym.f_nf[f], k = sym.f_k[f];
-            int kb = std::min(k, 32);      // largest staged block: the first (longest) kb rows
-            size_t usz = (size_t)kb * (nf + 1) - (size_t)kb * (kb - 1) / 2;
-            smem = std::max(smem, (usz + nf) * sizeof(double));
-            sl.max_nf = std::max(sl.max_nf, nf);
-            sl.max_k = std::max(sl.max_k, k);
+        int b = sym.depthptr[d], e = sym.depthptr[d + 1];
+        int i = b;
+        while (i < e) {
+            int j = e;
+            int c = 0;
+            if (S > 1) {
+                c = bcls(sym.f_nf[sym.depth_fronts[i]]);
+                j = i;
+                while (j < e && bcls(sym.f_nf[sym.depth_fronts[j]]) == c) ++j;
+            }
+            SolveLaunch sl{};
+            sl.begin = i;
+            sl.count = j - i;
+            size_t smem = 0, full = 0;
+            for (int q = i; q < j; ++q) {
+                int f = sym.depth_fronts[q];
+                int nf = sym.f_nf[f], k = sym.f_k[f];
+                int kb = std::min(k, 32);      // single-case kernel: largest staged block = the first kb rows
+                size_t usz = (size_t)kb * (nf + 1) - (size_t)kb * (kb - 1) / 2;
+                smem = std::max(smem, (usz + nf) * sizeof(double));
+                size_t uall = (size_t)k * (nf + 1) - (size_t)k * (k - 1) / 2;
+                full = std::max(full, (uall + nf) * sizeof(double));
+                sl.max_nf = std::max(sl.max_nf, nf);
+                sl.max_k = std::max(sl.max_k, k);
+            }
+            if (S > 1) {
+                sl.ts = std::min(brules[c].ts, S);
+                while (sl.ts > 1 && full * sl.ts > 100 * 1024) sl.ts /= 2;
+                smem = full * sl.ts;
+                if (smem > 200 * 1024) throw std::runtime_error("front too large for the batch back-solve");
+            } else {
+                sl.ts = 1;
+                if (smem > 100 * 1024) throw std::runtime_error("front too large for the back-solve staging buffer");
+            }
+            sl.smem = smem;
+            splan.push_back(sl);
+            i = j;
         }
-        sl.smem = smem;
-        if (smem > 100 * 1024) throw std::runtime_error("front too large for the back-solve staging buffer");
-        splan.push_back(sl);
     }
     d_U.alloc((size_t)sym.u_size * S);
     d_upd.alloc((size_t)sym.upd_size * S);
@@ -286,19 +642,23 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
     plan(S);
     for (const FactorLaunch& fl : fplan) {
         dim3 grid(fl.count, S / fl.ts);
-        mf_factor_kernel<<<grid, fl.threads, fl.smem, st>>>(dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
-                                                            d_upd.p, S, fl.ts, fl.tr, active, status,
-                                                            fl.global_front ? d_gwork.p : nullptr, fl.gstride);
+        if (fl.bulk)
+            launch_factor_bulk(fl.maxnf, grid, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
+                               d_upd.p, S, fl.smem_elems, active, status);
+        else if (fl.global_front)
+            launch_factor<true>(fl.ts, grid, fl.threads, 0, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
+                                d_upd.p, S, fl.tr, active, status, d_gwork.p, fl.gstride);
+        else
+            launch_factor<false>(fl.ts, grid, fl.threads, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs,
+                                 d_U.p, d_upd.p, S, fl.tr, active, status, nullptr, 0);
     }
     if (after_factor) JGB_CUDA(cudaEventRecord(after_factor, st));
     for (const SolveLaunch& sl : splan) {
         if (S == 1) {
             mf_backsolve_single<<<sl.count, 128, sl.smem, st>>>(dev, d_depth_fronts.p + sl.begin, d_U.p, x, active);
         } else {
-            long long work = (long long)sl.count * S;
-            int blocks = (int)((work + 127) / 128);
-            mf_backsolve_batch<<<blocks, 128, 0, st>>>(dev, d_depth_fronts.p + sl.begin, sl.count, d_U.p, x, S,
-                                                       active);
+            launch_backsolve_tile(sl.ts, dim3(sl.count, S / sl.ts), sl.smem, st, dev, d_depth_fronts.p + sl.begin,
+                                  d_U.p, x, S, active);
         }
     }
     JGB_CUDA(cudaGetLastError());

@@ -12,8 +12,9 @@ namespace jgb {
 
 struct DevSym {
     const int *f_k, *f_nf, *f_rowptr, *f_rows, *f_relptr, *f_rel, *f_childptr, *f_children, *f_asmptr, *asm_src,
-        *asm_dst;
+        *asm_dst, *f_eaptr, *ea_dst, *ea_srcptr, *ea_src;
     const long long *f_uoff, *f_updoff;
+    long long upd_size;
 };
 
 struct FactorLaunch {
@@ -23,12 +24,16 @@ struct FactorLaunch {
     int tr;                // row lanes (power of two), column lanes = threads / ts / tr
     size_t smem;
     bool global_front;     // front kept in a global workspace instead of shared memory
+    bool bulk;             // TMA-staged small-front kernel (batch only)
+    int maxnf;             // bulk: register bound on the front order (kernel variant)
+    int smem_elems;        // bulk: front + staging capacity in elements (x 32 lanes x 8 bytes)
     long long gstride;
 };
 
 struct SolveLaunch {
     int begin, count;      // range in depth_fronts
     int max_nf, max_k;
+    int ts;                // batch: scenarios per warp (32 / ts lanes cooperate on one scenario)
     size_t smem;           // S == 1 path only
 };
 
@@ -51,7 +56,7 @@ class MfSolver {
     std::vector<FactorLaunch> fplan;
     std::vector<SolveLaunch> splan;
     DevBuf<int> d_f_k, d_f_nf, d_f_rowptr, d_f_rows, d_f_relptr, d_f_rel, d_f_childptr, d_f_children, d_f_asmptr,
-        d_asm_src, d_asm_dst, d_level_fronts, d_depth_fronts;
+        d_asm_src, d_asm_dst, d_level_fronts, d_depth_fronts, d_f_eaptr, d_ea_dst, d_ea_srcptr, d_ea_src;
     DevBuf<long long> d_f_uoff, d_f_updoff;
     DevBuf<double> d_U, d_upd, d_gwork;
     DevSym dev{};

@@ -324,6 +324,38 @@ void analyse(int n, const int* colptr, const int* rowidx, const int* group, cons
     }
     S.u_size = uo;
     S.upd_size = po;
+    if (po >= (int64_t)1 << 31) throw std::runtime_error("symbolic: update storage exceeds 2^31 elements");
+    // ---- extend-add gather lists
+    {
+        S.f_eaptr.assign(nf_total + 1, 0);
+        S.ea_srcptr.clear();
+        std::vector<std::pair<int, int>> rec;   // (dst, src)
+        for (int f = 0; f < nf_total; ++f) {
+            rec.clear();
+            const int nf = S.f_nf[f];
+            for (int ci = S.f_childptr[f]; ci < S.f_childptr[f + 1]; ++ci) {
+                const int c = S.f_children[ci];
+                const int uc = S.f_nf[c] - S.f_k[c];
+                const int* rel = &S.f_rel[S.f_relptr[c]];
+                for (int j = 0; j <= uc; ++j) {
+                    const int dc = (j < uc) ? rel[j] : nf;
+                    for (int i = 0; i < uc; ++i)
+                        rec.push_back({rel[i] + dc * nf, (int)(S.f_updoff[c] + i + (int64_t)j * uc)});
+                }
+            }
+            std::stable_sort(rec.begin(), rec.end(),
+                             [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
+            for (size_t t = 0; t < rec.size(); ++t) {
+                if (t == 0 || rec[t].first != rec[t - 1].first) {
+                    S.ea_dst.push_back(rec[t].first);
+                    S.ea_srcptr.push_back((int)S.ea_src.size());
+                }
+                S.ea_src.push_back(rec[t].second);
+            }
+            S.f_eaptr[f + 1] = (int)S.ea_dst.size();
+        }
+        S.ea_srcptr.push_back((int)S.ea_src.size());
+    }
     // ---- level schedules
     std::vector<int> height(nf_total, 0), depth(nf_total, 0);
     for (int f = 0; f < nf_total; ++f)   // children precede parents (postorder)
@@ -355,16 +387,10 @@ int host_factor_solve(const Symbolic& S, const double* aval, const double* rhs, 
         F.assign((size_t)nf * (nf + 1), 0.0);
         for (int a = S.f_asmptr[f]; a < S.f_asmptr[f + 1]; ++a) F[S.asm_dst[a]] += aval[S.asm_src[a]];
         for (int p = 0; p < k; ++p) F[p + (size_t)nf * nf] = rhs[rows[p]];
-        for (int ci = S.f_childptr[f]; ci < S.f_childptr[f + 1]; ++ci) {
-            int c = S.f_children[ci];
-            int uc = S.f_nf[c] - S.f_k[c];
-            const int* rel = &S.f_rel[S.f_relptr[c]];
-            const double* C = &upd[S.f_updoff[c]];
-            for (int j = 0; j <= uc; ++j)
-                for (int i = 0; i < uc; ++i) {
-                    int dc = (j < uc) ? rel[j] : nf;
-                    F[rel[i] + (size_t)dc * nf] += C[i + (size_t)j * uc];
-                }
+        for (int d = S.f_eaptr[f]; d < S.f_eaptr[f + 1]; ++d) {
+            double acc = F[S.ea_dst[d]];
+            for (int t = S.ea_srcptr[d]; t < S.ea_srcptr[d + 1]; ++t) acc += upd[S.ea_src[t]];
+            F[S.ea_dst[d]] = acc;
         }
         for (int p = 0; p < k; ++p) {
             double piv = F[p + (size_t)p * nf];

