@@ -350,8 +350,8 @@ def run_ours(args):
     # algorithmic bytes of ONE factor phase for S scenarios: read J values + mismatch, write packed U rows, write and
     # read back every update block: 8 * (nnzJ + dim + u_size + 2 * upd_size) per scenario
     nnzj, dimj = ctx.stat("nr.nnz_j"), ctx.stat("nr.dim")
-    bytes_fac = 8.0 * (nnzj + dimj + ctx.stat("nr.u_size") + 2 * ctx.stat("nr.upd_size")) * S
-    fac_launches = ctx.stat("nr.factor_launches")
+    bytes_fac = 8.0 * (nnzj + dimj + ctx.stat("nr.batch.u_size") + 2 * ctx.stat("nr.batch.upd_size")) * S
+    fac_launches = ctx.stat("nr.batch.factor_launches")
     achieved = (bytes_fac * n_fac) / (t_fac * 1e-3) / 1e9 if t_fac > 0 else 0.0
     traffic = None
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")

@@ -270,9 +270,14 @@ void NrContext::setup(int64_t n_, const int64_t* ycp, const int64_t* yrv, const 
         if (pvpq[i] >= 0) group[pvpq[i]] = i;
         if (pq[i] >= 0) group[pq[i]] = i;
     }
-    Symbolic sym;
-    analyse(dim, jcp.data(), jrv.data(), group.data(), nullptr, SymbolicOptions(), sym);
-    solver.setup(sym, stream);
+    {
+        Symbolic sym;
+        analyse(dim, jcp.data(), jrv.data(), group.data(), nullptr, latency_options(), sym);
+        solver.setup(sym, stream);
+        Symbolic symb;
+        analyse(dim, jcp.data(), jrv.data(), group.data(), nullptr, throughput_options(), symb);
+        solver_batch.setup(symb, stream);
+    }
 
     // ---- device upload
     d_ycolptr.upload(cp, stream);
@@ -503,8 +508,8 @@ int NrContext::batch(int64_t Sreal64, const int64_t* of, const int64_t* ot, cons
         size_t f0 = timer.last();
         cudaEvent_t mid = timer.reserve();
         size_t f1 = timer.last();
-        solver.factor_solve(b_jval.p, b_f.p, b_inc.p, S, b_active.p, b_status.p, stream, mid);
-        launches += solver.launches_per_solve(S);
+        solver_batch.factor_solve(b_jval.p, b_f.p, b_inc.p, S, b_active.p, b_status.p, stream, mid);
+        launches += solver_batch.launches_per_solve(S);
         timer.mark(stream);
         size_t f2 = timer.last();
         timer.span(kPhFactor, f0, f1);
@@ -551,6 +556,19 @@ int NrContext::batch(int64_t Sreal64, const int64_t* of, const int64_t* ot, cons
 }
 
 double NrContext::stat(const std::string& key) {
+    if (key.rfind("nr.batch.", 0) == 0) {
+        const Symbolic& b = solver_batch.sym;
+        if (key == "nr.batch.u_size") return (double)b.u_size;
+        if (key == "nr.batch.upd_size") return (double)b.upd_size;
+        if (key == "nr.batch.fronts") return b.nfronts;
+        if (key == "nr.batch.levels") return b.nlevels;
+        if (key == "nr.batch.flops") return b.flops;
+        if (key == "nr.batch.nnz_lu") return (double)b.nnz_lu;
+        if (key == "nr.batch.max_front") return b.max_front;
+        if (key == "nr.batch.factor_launches") return solver_batch.factor_launches(32);
+        if (key == "nr.batch.launches_per_solve") return solver_batch.launches_per_solve(32);
+        return -1.0;
+    }
     const Symbolic& s = solver.sym;
     if (key == "nr.time.assemble_ms") return timer.ms[kPhAssemble];
     if (key == "nr.time.factor_ms") return timer.ms[kPhFactor];

@@ -66,7 +66,8 @@ class NrContext {
     NrDev view(int S, bool batch);
 
     cudaStream_t stream;
-    MfSolver solver;
+    MfSolver solver;         // single case (latency-oriented amalgamation)
+    MfSolver solver_batch;   // scenario batches (throughput-oriented amalgamation)
     DevBuf<int> d_ycolptr, d_yrow, d_pq, d_pvpq, d_pcount, d_jcolptr;
     DevBuf<double2> d_y, d_yt;
     DevBuf<signed char> d_type;

@@ -103,6 +103,93 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __rest
     }
 }
 
+// ---- column-in-registers variant for mid-size fronts (batch): TE = blockDim / TS lanes per scenario, lane e owns
+// column e of the front (nf + 1 <= TE columns incl. rhs) in registers; the pivot column is broadcast through a
+// shared-memory strip, so a multiply-add costs one LDS (broadcast) + one DFMA instead of two LDS + STS + index math.
+template <int TS, int MAXNF>
+__global__ void __launch_bounds__(256)
+mf_factor_col_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ aval,
+                     const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S,
+                     const unsigned char* __restrict__ active, int* __restrict__ status) {
+    extern __shared__ double Fs[];
+    const int sl = threadIdx.x % TS, e0 = threadIdx.x / TS;
+    constexpr int TE = 256 / TS;
+    static_assert(TE >= MAXNF + 1, "one lane per column");
+    double* Fl = Fs + sl;
+    const int f = fronts[blockIdx.x];
+    const int s = blockIdx.y * TS + sl;
+    const bool act = active ? (active[s] != 0) : true;
+    if (!__syncthreads_or(act)) return;
+    const int nf = sy.f_nf[f], k = sy.f_k[f], u = nf - k;
+    const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
+    const int total = nf * (nf + 1);
+    for (int pos = e0; pos < total; pos += TE) Fl[pos * TS] = 0.0;
+    __syncthreads();
+    if (act) {
+        const double* __restrict__ av = aval + s;
+        const int a1 = sy.f_asmptr[f + 1];
+        for (int a = sy.f_asmptr[f] + e0; a < a1; a += TE) Fl[sy.asm_dst[a] * TS] = av[(long long)sy.asm_src[a] * S];
+        for (int p = e0; p < k; p += TE) Fl[(p + nf * nf) * TS] = rhs[(long long)rows[p] * S + s];
+    }
+    __syncthreads();
+    const int W = S < 32 ? S : 32;
+    double* __restrict__ up = upd + (long long)(s / W) * sy.upd_size * W + (s % W);
+    if (act) {
+        const int d1 = sy.f_eaptr[f + 1];
+        for (int d = sy.f_eaptr[f] + e0; d < d1; d += TE) {
+            const int dst = sy.ea_dst[d] * TS;
+            double acc = Fl[dst];
+            const int t1 = sy.ea_srcptr[d + 1];
+            for (int t = sy.ea_srcptr[d]; t < t1; ++t) acc += up[(long long)sy.ea_src[t] * W];
+            Fl[dst] = acc;
+        }
+    }
+    __syncthreads();
+    const int c = e0;                        // my column
+    const bool mine = c <= nf;
+    double col[MAXNF];
+#pragma unroll
+    for (int i = 0; i < MAXNF; ++i) col[i] = (mine && i < nf) ? Fl[(i + c * nf) * TS] : 0.0;
+    __syncthreads();                         // the front area is reused as the broadcast strip from here on
+    double* bc = Fs + sl;                    // 2 x MAXNF x TS doubles
+    double cur = col[0];                     // col[p] of the running pivot row
+    bool bad = false;
+    double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
+    for (int p = 0; p < k; ++p) {
+        double* b = bc + (p & 1) * (MAXNF * TS);
+        if (c == p) {
+#pragma unroll
+            for (int i = 0; i < MAXNF; ++i)
+                if (i >= p && i < nf) b[i * TS] = col[i];
+        }
+        __syncthreads();
+        const double piv = b[p * TS];
+        if (piv == 0.0 || !isfinite(piv)) bad = true;
+        const double inv = 1.0 / piv;
+        if (act && mine && c >= p) Uf[(urow_off(p, nf) + (c - p)) * S] = (c == p) ? inv : cur;
+        const double m = (mine && c > p) ? inv * cur : 0.0;
+        double nxt = 0.0;
+#pragma unroll
+        for (int i0 = 0; i0 < MAXNF; i0 += 8) {
+            if (i0 + 8 <= p + 1) continue;           // whole chunk above the pivot row: nothing to do (uniform)
+#pragma unroll
+            for (int i = i0; i < i0 + 8; ++i) {
+                if (i > p) col[i] -= b[i * TS] * m;  // rows >= nf hold zeros in b? no: guard through m / zero columns
+                if (i == p + 1) nxt = col[i];
+            }
+        }
+        cur = nxt;
+    }
+    if (!act) return;
+    if (bad && e0 == 0) status[s] = -3;
+    if (mine && c >= k) {
+        double* Cj = up + (sy.f_updoff[f] + (long long)(c - k) * u) * W;
+#pragma unroll
+        for (int i = 0; i < MAXNF; ++i)
+            if (i >= k && i < nf) Cj[(long long)(i - k) * W] = col[i];
+    }
+}
+
 // ---- TMA-staged variant for the many small fronts of a batch -------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -293,6 +380,17 @@ void launch_factor(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st,
 #undef JGB_CASE
 }
 
+void launch_factor_col(int maxnf, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const int* fronts,
+                       const double* aval, const double* rhs, double* U, double* upd, int S,
+                       const unsigned char* active, int* status) {
+    if (maxnf == 31)
+        mf_factor_col_kernel<8, 31><<<grid, 256, smem, st>>>(dev, fronts, aval, rhs, U, upd, S, active, status);
+    else if (maxnf == 63)
+        mf_factor_col_kernel<4, 63><<<grid, 256, smem, st>>>(dev, fronts, aval, rhs, U, upd, S, active, status);
+    else
+        throw std::runtime_error("unsupported column-register factor variant");
+}
+
 // (lanes per scenario, register bound on the front order) variants of the bulk kernel
 #define JGB_BULK_VARIANTS(X) X(4, 8) X(4, 12) X(8, 16) X(8, 20)
 
@@ -470,6 +568,8 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st) {
     JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JGB_CUDA(cudaFuncSetAttribute(mf_factor_col_kernel<8, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JGB_CUDA(cudaFuncSetAttribute(mf_factor_col_kernel<4, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 #define X(TE, MAXNF) \
     JGB_CUDA(cudaFuncSetAttribute(mf_factor_bulk_kernel<TE, MAXNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     JGB_BULK_VARIANTS(X)
@@ -511,6 +611,8 @@ void MfSolver::plan(int S) {
                                                       {96, 1, 256}, {kMaxSmemFront, 1, 256}};
     const char* nb = getenv("JGB_NO_BULK");
     const bool bulk_enabled = !(nb && *nb == '1');
+    const char* nc = getenv("JGB_COLREG");     // experimental column-in-registers kernel: off unless JGB_COLREG=1
+    const bool colreg_enabled = (nc && *nc == '1');
     const std::vector<PlanRule> rules = (S == 1) ? parse_rules("JGB_FPLAN_SINGLE", single_rules)
                                                  : parse_rules("JGB_FPLAN_BATCH", batch_rules);
     auto cls = [&](int nf) { size_t c = 0; while (c < rules.size() && nf > rules[c].maxnf) ++c; return (int)c; };
@@ -553,7 +655,15 @@ void MfSolver::plan(int S) {
                     fl.smem = bytes;
                 }
             }
-            if (fl.bulk) {
+            fl.colreg = 0;
+            if (!fl.bulk && !fl.global_front && S >= 32 && colreg_enabled && nf <= 63) {
+                fl.colreg = rules[c].maxnf <= 32 ? 31 : 63;
+                if (nf > fl.colreg) fl.colreg = 63;
+                fl.ts = fl.colreg == 31 ? 8 : 4;
+                fl.threads = 256;
+                fl.smem = std::max(per * fl.ts, (size_t)2 * (fl.colreg + 1) * fl.ts * sizeof(double));
+            }
+            if (fl.bulk || fl.colreg) {
             } else if (fl.global_front) {
                 fl.ts = (S == 1) ? 1 : 4;
                 fl.threads = 256;
@@ -564,7 +674,7 @@ void MfSolver::plan(int S) {
             }
             int te = fl.threads / fl.ts;
             fl.tr = std::min(pow2_floor(te), 16);
-            if (!fl.bulk) fl.smem = fl.global_front ? 0 : per * fl.ts;
+            if (!fl.bulk && !fl.colreg) fl.smem = fl.global_front ? 0 : per * fl.ts;
             fl.gstride = (long long)nf * (nf + 1) * fl.ts;
             if (fl.global_front)
                 gwork_need = std::max<size_t>(gwork_need, (size_t)fl.gstride * fl.count * (S / fl.ts));
@@ -645,6 +755,9 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
         if (fl.bulk)
             launch_factor_bulk(fl.maxnf, grid, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
                                d_upd.p, S, fl.smem_elems, active, status);
+        else if (fl.colreg)
+            launch_factor_col(fl.colreg, grid, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p, d_upd.p,
+                              S, active, status);
         else if (fl.global_front)
             launch_factor<true>(fl.ts, grid, fl.threads, 0, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
                                 d_upd.p, S, fl.tr, active, status, d_gwork.p, fl.gstride);

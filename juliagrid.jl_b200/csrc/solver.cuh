@@ -25,6 +25,7 @@ struct FactorLaunch {
     size_t smem;
     bool global_front;     // front kept in a global workspace instead of shared memory
     bool bulk;             // TMA-staged small-front kernel (batch only)
+    int colreg;            // column-in-registers kernel variant (0 = not used)
     int maxnf;             // bulk: register bound on the front order (kernel variant)
     int smem_elems;        // bulk: front + staging capacity in elements (x 32 lanes x 8 bytes)
     long long gstride;

@@ -5,6 +5,8 @@
 #include <algorithm>
 #include <cassert>
 #include <cmath>
+#include <cstdio>
+#include <cstdlib>
 #include <numeric>
 #include <set>
 #include <stdexcept>
@@ -95,7 +97,12 @@ void column_structures(int n, const std::vector<std::vector<int>>& sadj, const s
 }  // namespace
 
 void analyse(int n, const int* colptr, const int* rowidx, const int* group, const unsigned char* /*skip*/,
-             const SymbolicOptions& opt, Symbolic& S) {
+             const SymbolicOptions& opt_in, Symbolic& S) {
+    SymbolicOptions opt = opt_in;
+    if (const char* env = getenv("JGB_RELAX")) {   // tuning experiments: small,mid,midfrac,big,bigfrac,anyfrac
+        sscanf(env, "%d,%d,%lf,%d,%lf,%lf", &opt.relax_small, &opt.relax_mid, &opt.relax_mid_frac, &opt.relax_big,
+               &opt.relax_big_frac, &opt.relax_any_frac);
+    }
     S = Symbolic();
     S.n = n;
     // ---- symmetric scalar graph (no diagonal)

@@ -20,6 +20,16 @@ struct SymbolicOptions {
     double relax_any_frac = 0.05;
 };
 
+// Amalgamation presets: a single case is latency bound (fewer, larger fronts = fewer levels and launches), a batch
+// is throughput bound (less amalgamation = fewer explicit zeros and flops).
+inline SymbolicOptions latency_options() { return SymbolicOptions(); }
+inline SymbolicOptions throughput_options() {
+    SymbolicOptions o;
+    o.relax_small = 2; o.relax_mid = 8; o.relax_mid_frac = 0.3; o.relax_big = 24; o.relax_big_frac = 0.1;
+    o.relax_any_frac = 0.02;
+    return o;
+}
+
 struct Symbolic {
     int n = 0;                       // scalar dimension
     std::vector<int> perm;           // elimination position -> original variable

@@ -603,9 +603,14 @@ void WlsContext::setup(int64_t n_, int64_t m_, int64_t slack_, const int64_t* hc
     // ---- symbolic factorisation of G: theta_i and V_i of one bus form a supervariable
     std::vector<int> group(nv);
     for (int i = 0; i < n; ++i) { group[i] = i; group[i + n] = i; }
-    Symbolic sym;
-    analyse(nv, gcolptr.data(), grow.data(), group.data(), nullptr, SymbolicOptions(), sym);
-    solver.setup(sym, stream);
+    {
+        Symbolic sym;
+        analyse(nv, gcolptr.data(), grow.data(), group.data(), nullptr, latency_options(), sym);
+        solver.setup(sym, stream);
+        Symbolic symb;
+        analyse(nv, gcolptr.data(), grow.data(), group.data(), nullptr, throughput_options(), symb);
+        solver_batch.setup(symb, stream);
+    }
     // ---- branch coefficients
     std::vector<double> bg(nbr), bb(nbr), bgsi(nbr), bbsi(nbr), btinv(nbr), bphi(nbr);
     for (int k = 0; k < nbr; ++k) {
@@ -722,8 +727,9 @@ void WlsContext::launch_gain(int S, bool batch) {
     const size_t g1 = timer.last();
     cudaEvent_t mid = timer.reserve();
     const size_t g2 = timer.last();
-    solver.factor_solve(d.gval, d.rhs, d.inc, S, batch ? d.active : nullptr, d.status, stream, mid);
-    launches += solver.launches_per_solve(S);
+    MfSolver& sv = batch ? solver_batch : solver;
+    sv.factor_solve(d.gval, d.rhs, d.inc, S, batch ? d.active : nullptr, d.status, stream, mid);
+    launches += sv.launches_per_solve(S);
     timer.mark(stream);
     const size_t g3 = timer.last();
     timer.span(kPhGain, g0, g1);

@@ -88,7 +88,8 @@ class WlsContext {
     void alloc_batch(int S);
 
     cudaStream_t stream;
-    MfSolver solver;
+    MfSolver solver;         // single case
+    MfSolver solver_batch;   // Monte-Carlo batches
     DevBuf<int> d_ycolptr, d_yrow, d_ydiag, d_br_from, d_br_to, d_index, d_slotptr, d_slotpos, d_hcolptr, d_hrow,
         d_gentry_ptr, d_gterm_a, d_gterm_b, d_gterm_w, d_glow_pos, d_gup_pos;
     DevBuf<double2> d_y, d_yt;
