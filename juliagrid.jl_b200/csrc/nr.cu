@@ -442,9 +442,18 @@ int NrContext::run(int64_t max_iter, double tol, int64_t* iters, double* sp, dou
         JGB_CUDA(cudaMemcpyAsync(h_int.p + 1, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         d_stop.download(h_stop.p, 2, stream);
         JGB_CUDA(cudaStreamSynchronize(stream));
+        timer.resolve();
         if (h_int.p[0] == 0) { rc = h_int.p[1]; break; }
-        solver.factor_solve(d_jval.p, d_f.p, d_inc.p, 1, d_active.p, d_status.p, stream);
+        timer.mark(stream);
+        const size_t f0 = timer.last();
+        cudaEvent_t mid = timer.reserve();
+        const size_t f1 = timer.last();
+        solver.factor_solve(d_jval.p, d_f.p, d_inc.p, 1, d_active.p, d_status.p, stream, mid);
         launches += solver.launches_per_solve(1);
+        timer.mark(stream);
+        const size_t f2 = timer.last();
+        timer.span(kPhFactor, f0, f1);
+        timer.span(kPhBacksolve, f1, f2);
         nr_update_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(d, 1);
         ++launches;
         iteration += 1;

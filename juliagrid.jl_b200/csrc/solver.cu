@@ -55,33 +55,78 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __rest
         for (int p = e0; p < k; p += TE) Fl[(p + nf * nf) * TS] = rhs[(long long)rows[p] * S + s];
     }
     __syncthreads();
-    // extend-add of all children as one gather: each destination sums its sources in child order (deterministic),
-    // destinations are distinct, so no barrier is needed between children
+    // extend-add of all children as a gather in rounds (child order per destination, so sums are deterministic)
     // update storage is tile major: element e of scenario s at [((s / W) * upd_size + e) * W + s % W], W = min(S, 32)
     const int W = S < 32 ? S : 32;
     double* __restrict__ up = upd + (long long)(s / W) * sy.upd_size * W + (s % W);
-    if (act) {
-        const int d1 = sy.f_eaptr[f + 1];
-        for (int d = sy.f_eaptr[f] + e0; d < d1; d += TE) {
-            const int dst = sy.ea_dst[d] * TS;
-            double acc = Fl[dst];
-            const int t1 = sy.ea_srcptr[d + 1];
-            for (int t = sy.ea_srcptr[d]; t < t1; ++t) acc += up[(long long)sy.ea_src[t] * W];
-            Fl[dst] = acc;
+    {
+        const int r1 = sy.f_eaptr[f + 1];
+        for (int r = sy.f_eaptr[f]; r < r1; ++r) {      // rounds: distinct destinations inside a round
+            const int t1 = sy.ea_roundptr[r + 1];
+            if (act) {
+#pragma unroll 4
+                for (int t = sy.ea_roundptr[r] + e0; t < t1; t += TE) {
+                    const int2 pr = sy.ea_pair[t];
+                    Fl[pr.x * TS] += up[(long long)pr.y * W];
+                }
+            }
+            __syncthreads();
         }
     }
-    __syncthreads();
     bool bad = false;
     const int colstride = nf * TS;
-    for (int p = 0; p < k; ++p) {
-        const double* colp = Fl + p * colstride;
-        const double piv = colp[p * TS];
-        if (piv == 0.0 || !isfinite(piv)) bad = true;
-        const double inv = 1.0 / piv;
-        for (int j = p + 1 + ec; j <= nf; j += TC) {
+    // Blocked right-looking elimination, panels of B pivots:
+    //  (a) panel: rank-1 steps restricted to the panel columns (one barrier each, a handful of multiply-adds per
+    //      row), the multipliers l_i = F[i,p] / F[p,p] overwrite column p (L is not an output);
+    //  (b) U12 = L11^-1 A12: one lane per trailing column (incl. the rhs column), no barrier inside;
+    //  (c) A22 -= L21 U12: row-owner lanes keep their B multipliers in registers and sweep the columns — the pivot-row
+    //      reads are shared-memory broadcasts, ~2 instructions per multiply-add.
+    constexpr int B = 8;
+    for (int p0 = 0; p0 < k; p0 += B) {
+        const int pe = (p0 + B < k) ? p0 + B : k;
+        for (int p = p0; p < pe; ++p) {
+            const double piv = Fl[(p + p * nf) * TS];
+            if (piv == 0.0 || !isfinite(piv)) bad = true;
+            const double inv = 1.0 / piv;
+            for (int i = p + 1 + e0; i < nf; i += TE) {
+                double* rowi = Fl + i * TS;
+                const double li = rowi[p * colstride] * inv;
+                rowi[p * colstride] = li;
+                for (int j = p + 1; j < pe; ++j) rowi[j * colstride] -= li * Fl[(p + j * nf) * TS];
+            }
+            __syncthreads();
+        }
+        for (int j = pe + e0; j <= nf; j += TE) {
             double* colj = Fl + j * colstride;
-            const double m = inv * colj[p * TS];
-            for (int i = p + 1 + er; i < nf; i += TR) colj[i * TS] -= colp[i * TS] * m;
+            for (int q = p0; q < pe - 1; ++q) {
+                const double uq = colj[q * TS];
+                const double* lq = Fl + q * colstride;
+                for (int r = q + 1; r < pe; ++r) colj[r * TS] -= lq[r * TS] * uq;
+            }
+        }
+        __syncthreads();
+        const int pb = pe - p0;
+        for (int i = pe + er; i < nf; i += TR) {
+            double* rowi = Fl + i * TS;
+            double l[B];
+#pragma unroll
+            for (int q = 0; q < B; ++q) l[q] = (q < pb) ? rowi[(p0 + q) * colstride] : 0.0;
+            if (pb == B) {
+                for (int j = pe + ec; j <= nf; j += TC) {
+                    const double* uj = Fl + (p0 + j * nf) * TS;
+                    double acc = rowi[j * colstride];
+#pragma unroll
+                    for (int q = 0; q < B; ++q) acc -= l[q] * uj[q * TS];
+                    rowi[j * colstride] = acc;
+                }
+            } else {
+                for (int j = pe + ec; j <= nf; j += TC) {
+                    const double* uj = Fl + (p0 + j * nf) * TS;
+                    double acc = rowi[j * colstride];
+                    for (int q = 0; q < pb; ++q) acc -= l[q] * uj[q * TS];
+                    rowi[j * colstride] = acc;
+                }
+            }
         }
         __syncthreads();
     }
@@ -134,17 +179,20 @@ mf_factor_col_kernel(DevSym sy, const int* __restrict__ fronts, const double* __
     __syncthreads();
     const int W = S < 32 ? S : 32;
     double* __restrict__ up = upd + (long long)(s / W) * sy.upd_size * W + (s % W);
-    if (act) {
-        const int d1 = sy.f_eaptr[f + 1];
-        for (int d = sy.f_eaptr[f] + e0; d < d1; d += TE) {
-            const int dst = sy.ea_dst[d] * TS;
-            double acc = Fl[dst];
-            const int t1 = sy.ea_srcptr[d + 1];
-            for (int t = sy.ea_srcptr[d]; t < t1; ++t) acc += up[(long long)sy.ea_src[t] * W];
-            Fl[dst] = acc;
+    {
+        const int r1 = sy.f_eaptr[f + 1];
+        for (int r = sy.f_eaptr[f]; r < r1; ++r) {      // rounds: distinct destinations inside a round
+            const int t1 = sy.ea_roundptr[r + 1];
+            if (act) {
+#pragma unroll 4
+                for (int t = sy.ea_roundptr[r] + e0; t < t1; t += TE) {
+                    const int2 pr = sy.ea_pair[t];
+                    Fl[pr.x * TS] += up[(long long)pr.y * W];
+                }
+            }
+            __syncthreads();
         }
     }
-    __syncthreads();
     const int c = e0;                        // my column
     const bool mine = c <= nf;
     double col[MAXNF];
@@ -545,9 +593,8 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st) {
     d_asm_src.upload(sym.asm_src, st);
     d_asm_dst.upload(sym.asm_dst, st);
     d_f_eaptr.upload(sym.f_eaptr, st);
-    d_ea_dst.upload(sym.ea_dst, st);
-    d_ea_srcptr.upload(sym.ea_srcptr, st);
-    d_ea_src.upload(sym.ea_src, st);
+    d_ea_roundptr.upload(sym.ea_roundptr, st);
+    d_ea_pair.upload(sym.ea_pair, st);
     d_level_fronts.upload(sym.level_fronts, st);
     d_depth_fronts.upload(sym.depth_fronts, st);
     std::vector<long long> uo(sym.f_uoff.begin(), sym.f_uoff.end()), po(sym.f_updoff.begin(), sym.f_updoff.end());
@@ -558,7 +605,8 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st) {
     dev.f_relptr = d_f_relptr.p; dev.f_rel = d_f_rel.p; dev.f_childptr = d_f_childptr.p;
     dev.f_children = d_f_children.p; dev.f_asmptr = d_f_asmptr.p; dev.asm_src = d_asm_src.p;
     dev.asm_dst = d_asm_dst.p; dev.f_uoff = d_f_uoff.p; dev.f_updoff = d_f_updoff.p;
-    dev.f_eaptr = d_f_eaptr.p; dev.ea_dst = d_ea_dst.p; dev.ea_srcptr = d_ea_srcptr.p; dev.ea_src = d_ea_src.p;
+    dev.f_eaptr = d_f_eaptr.p; dev.ea_roundptr = d_ea_roundptr.p;
+    dev.ea_pair = reinterpret_cast<const int2*>(d_ea_pair.p);
     planned_S = -1;
     set_factor_smem_attr<1>(); set_factor_smem_attr<2>(); set_factor_smem_attr<4>();
     set_factor_smem_attr<8>(); set_factor_smem_attr<16>(); set_factor_smem_attr<32>();
@@ -673,7 +721,9 @@ void MfSolver::plan(int S) {
                 while (fl.ts > 1 && per * fl.ts > 200 * 1024) fl.ts /= 2;
             }
             int te = fl.threads / fl.ts;
-            fl.tr = std::min(pow2_floor(te), 16);
+            int trw = 1;
+            while (trw < nf && trw < te) trw *= 2;     // rows first: one lane per front row when the lanes allow
+            fl.tr = std::min(pow2_floor(te), trw);
             if (!fl.bulk && !fl.colreg) fl.smem = fl.global_front ? 0 : per * fl.ts;
             fl.gstride = (long long)nf * (nf + 1) * fl.ts;
             if (fl.global_front)

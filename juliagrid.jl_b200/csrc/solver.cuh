@@ -12,7 +12,8 @@ namespace jgb {
 
 struct DevSym {
     const int *f_k, *f_nf, *f_rowptr, *f_rows, *f_relptr, *f_rel, *f_childptr, *f_children, *f_asmptr, *asm_src,
-        *asm_dst, *f_eaptr, *ea_dst, *ea_srcptr, *ea_src;
+        *asm_dst, *f_eaptr, *ea_roundptr;
+    const int2* ea_pair;
     const long long *f_uoff, *f_updoff;
     long long upd_size;
 };
@@ -57,7 +58,7 @@ class MfSolver {
     std::vector<FactorLaunch> fplan;
     std::vector<SolveLaunch> splan;
     DevBuf<int> d_f_k, d_f_nf, d_f_rowptr, d_f_rows, d_f_relptr, d_f_rel, d_f_childptr, d_f_children, d_f_asmptr,
-        d_asm_src, d_asm_dst, d_level_fronts, d_depth_fronts, d_f_eaptr, d_ea_dst, d_ea_srcptr, d_ea_src;
+        d_asm_src, d_asm_dst, d_level_fronts, d_depth_fronts, d_f_eaptr, d_ea_roundptr, d_ea_pair;
     DevBuf<long long> d_f_uoff, d_f_updoff;
     DevBuf<double> d_U, d_upd, d_gwork;
     DevSym dev{};

@@ -332,11 +332,12 @@ void analyse(int n, const int* colptr, const int* rowidx, const int* group, cons
     S.u_size = uo;
     S.upd_size = po;
     if (po >= (int64_t)1 << 31) throw std::runtime_error("symbolic: update storage exceeds 2^31 elements");
-    // ---- extend-add gather lists
+    // ---- extend-add gather lists, organised in rounds (see symbolic.hpp)
     {
         S.f_eaptr.assign(nf_total + 1, 0);
-        S.ea_srcptr.clear();
-        std::vector<std::pair<int, int>> rec;   // (dst, src)
+        S.ea_roundptr.assign(1, 0);
+        std::vector<std::pair<int, int>> rec;   // (dst, src) in child order
+        std::vector<int> seen;                  // number of sources already met per destination
         for (int f = 0; f < nf_total; ++f) {
             rec.clear();
             const int nf = S.f_nf[f];
@@ -350,18 +351,20 @@ void analyse(int n, const int* colptr, const int* rowidx, const int* group, cons
                         rec.push_back({rel[i] + dc * nf, (int)(S.f_updoff[c] + i + (int64_t)j * uc)});
                 }
             }
-            std::stable_sort(rec.begin(), rec.end(),
-                             [](const std::pair<int, int>& a, const std::pair<int, int>& b) { return a.first < b.first; });
-            for (size_t t = 0; t < rec.size(); ++t) {
-                if (t == 0 || rec[t].first != rec[t - 1].first) {
-                    S.ea_dst.push_back(rec[t].first);
-                    S.ea_srcptr.push_back((int)S.ea_src.size());
-                }
-                S.ea_src.push_back(rec[t].second);
+            seen.assign((size_t)nf * (nf + 1), 0);
+            std::vector<std::vector<std::pair<int, int>>> rounds;
+            for (auto& pr : rec) {
+                int r = seen[pr.first]++;
+                if ((int)rounds.size() <= r) rounds.resize(r + 1);
+                rounds[r].push_back(pr);
             }
-            S.f_eaptr[f + 1] = (int)S.ea_dst.size();
+            for (auto& rd : rounds) {
+                std::sort(rd.begin(), rd.end());
+                for (auto& pr : rd) { S.ea_pair.push_back(pr.first); S.ea_pair.push_back(pr.second); }
+                S.ea_roundptr.push_back((int)(S.ea_pair.size() / 2));
+            }
+            S.f_eaptr[f + 1] = (int)S.ea_roundptr.size() - 1;
         }
-        S.ea_srcptr.push_back((int)S.ea_src.size());
     }
     // ---- level schedules
     std::vector<int> height(nf_total, 0), depth(nf_total, 0);
@@ -394,11 +397,9 @@ int host_factor_solve(const Symbolic& S, const double* aval, const double* rhs, 
         F.assign((size_t)nf * (nf + 1), 0.0);
         for (int a = S.f_asmptr[f]; a < S.f_asmptr[f + 1]; ++a) F[S.asm_dst[a]] += aval[S.asm_src[a]];
         for (int p = 0; p < k; ++p) F[p + (size_t)nf * nf] = rhs[rows[p]];
-        for (int d = S.f_eaptr[f]; d < S.f_eaptr[f + 1]; ++d) {
-            double acc = F[S.ea_dst[d]];
-            for (int t = S.ea_srcptr[d]; t < S.ea_srcptr[d + 1]; ++t) acc += upd[S.ea_src[t]];
-            F[S.ea_dst[d]] = acc;
-        }
+        for (int r = S.f_eaptr[f]; r < S.f_eaptr[f + 1]; ++r)
+            for (int t = S.ea_roundptr[r]; t < S.ea_roundptr[r + 1]; ++t)
+                F[S.ea_pair[2 * t]] += upd[S.ea_pair[2 * t + 1]];
         for (int p = 0; p < k; ++p) {
             double piv = F[p + (size_t)p * nf];
             if (piv == 0.0 || !std::isfinite(piv)) return -3;

@@ -50,10 +50,12 @@ struct Symbolic {
     std::vector<int> asm_dst;        // r + c*nf inside the front (column major, leading dimension nf)
     // extend-add as a gather: for every front, the destinations that receive child contributions and, per
     // destination, the source offsets into the update storage (children in order, so sums are deterministic)
-    std::vector<int> f_eaptr;        // [nfronts+1] range of destinations of a front in ea_dst / ea_srcptr
-    std::vector<int> ea_dst;         // destination position r + c*nf inside the parent front
-    std::vector<int> ea_srcptr;      // [ndst+1] range of sources of a destination in ea_src
-    std::vector<int> ea_src;         // element offset into the update storage (f_updoff[child] + i + j*u_child)
+    // Stored as rounds: round r of a front holds the r-th source of every destination that has one, so inside a round
+    // all destinations are distinct (no race, one barrier between rounds) and a record is a single (dst, src) pair.
+    std::vector<int> f_eaptr;        // [nfronts+1] range of rounds of a front in ea_roundptr
+    std::vector<int> ea_roundptr;    // [nrounds+1] range of pairs of a round in ea_pair
+    std::vector<int> ea_pair;        // 2 ints per pair: destination r + c*nf in the parent front, source element
+                                     // offset into the update storage (f_updoff[child] + i + j*u_child)
     std::vector<int64_t> f_uoff;     // offset of the front's packed U rows (k rows, row p has nf+1-p entries)
     std::vector<int64_t> f_updoff;   // offset of the front's update block (u x (u+1), column major, last col = rhs)
     int64_t u_size = 0, upd_size = 0;

@@ -17,7 +17,11 @@ if "single" in sys.argv:
         torch.cuda.synchronize(); t = time.perf_counter()
         ok = jgb200.power_flow(a)
         torch.cuda.synchronize(); dt = time.perf_counter() - t
-    print("single NR", ok, a.method.iteration, f"{dt*1e3:.2f} ms -> {a.method.iteration/dt:.0f} it/s")
+    lib.jgb_profile(ctx.handle, 1)
+    jgb200.set_initial_point(a); a._push_state(); jgb200.power_flow(a)
+    nfc = max(1.0, ctx.stat("nr.time.factor_count"))
+    print("single NR", ok, a.method.iteration, f"{dt*1e3:.2f} ms -> {a.method.iteration/dt:.0f} it/s | per iteration GPU: factor {ctx.stat('nr.time.factor_ms')/nfc*1e3:.0f} us, backsolve {ctx.stat('nr.time.backsolve_ms')/nfc*1e3:.0f} us")
+    lib.jgb_profile(ctx.handle, 0)
 jgb200.set_initial_point(a); a._push_state()
 elig = jgb200.eligible_outages(ps)
 of, ot, dy = jgb200.outage_arrays(ps, elig[:S])
