@@ -82,50 +82,89 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __rest
     //  (c) A22 -= L21 U12: row-owner lanes keep their B multipliers in registers and sweep the columns — the pivot-row
     //      reads are shared-memory broadcasts, ~2 instructions per multiply-add.
     constexpr int B = 8;
+    // Fronts kept in global memory (GLOBAL_F) stage the current panel (nf x B) and the U12 strip (B x (nf+1)) in
+    // shared memory, so the barrier-separated panel steps never wait on L2 round trips.
+    double* Pl = Fs + sl;                               // GLOBAL_F: panel, element (i, q) at Pl[(i + q*nf) * TS]
+    double* Ul = Fs + (size_t)nf * B * TS + sl;         // GLOBAL_F: strip, element (q, j) at Ul[(q + j*B) * TS]
     for (int p0 = 0; p0 < k; p0 += B) {
         const int pe = (p0 + B < k) ? p0 + B : k;
+        const int pb = pe - p0;
+        double* pan;          // panel base: element (i, p) at pan[(i + (p - p0)*nf) * TS]
+        if constexpr (GLOBAL_F) {
+            for (int t = e0; t < nf * pb; t += TE) Pl[t * TS] = Fl[(p0 * nf + t) * TS];
+            __syncthreads();
+            pan = Pl;
+        } else {
+            pan = Fl + p0 * colstride;
+        }
         for (int p = p0; p < pe; ++p) {
-            const double piv = Fl[(p + p * nf) * TS];
+            const double* colp = pan + (p - p0) * colstride;
+            const double piv = colp[p * TS];
             if (piv == 0.0 || !isfinite(piv)) bad = true;
             const double inv = 1.0 / piv;
             for (int i = p + 1 + e0; i < nf; i += TE) {
-                double* rowi = Fl + i * TS;
-                const double li = rowi[p * colstride] * inv;
-                rowi[p * colstride] = li;
-                for (int j = p + 1; j < pe; ++j) rowi[j * colstride] -= li * Fl[(p + j * nf) * TS];
+                double* rowi = pan + i * TS;
+                const double li = rowi[(p - p0) * colstride] * inv;
+                rowi[(p - p0) * colstride] = li;
+                for (int j = p + 1; j < pe; ++j) rowi[(j - p0) * colstride] -= li * pan[(p + (j - p0) * nf) * TS];
             }
             __syncthreads();
         }
-        for (int j = pe + e0; j <= nf; j += TE) {
-            double* colj = Fl + j * colstride;
-            for (int q = p0; q < pe - 1; ++q) {
-                const double uq = colj[q * TS];
-                const double* lq = Fl + q * colstride;
-                for (int r = q + 1; r < pe; ++r) colj[r * TS] -= lq[r * TS] * uq;
+        if constexpr (GLOBAL_F) {      // rows p0..pe-1 of the panel hold final U entries: back to the front
+            for (int t = e0; t < pb * pb; t += TE) {
+                const int r = p0 + t % pb, q = t / pb;
+                Fl[(r + (p0 + q) * nf) * TS] = Pl[(r + q * nf) * TS];
+            }
+        }
+        if constexpr (GLOBAL_F) {
+            for (int j = pe + e0; j <= nf; j += TE) {
+                double* colj = Fl + j * colstride;
+                double uq[B];
+#pragma unroll
+                for (int q = 0; q < B; ++q) uq[q] = (q < pb) ? colj[(p0 + q) * TS] : 0.0;
+#pragma unroll
+                for (int q = 0; q < B; ++q) {
+                    if (q < pb) {
+                        const double* lq = pan + q * colstride;
+#pragma unroll
+                        for (int r = q + 1; r < B; ++r)
+                            if (r < pb) uq[r] -= lq[(p0 + r) * TS] * uq[q];
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < B; ++q) {
+                    if (q < pb) {
+                        colj[(p0 + q) * TS] = uq[q];
+                        Ul[(q + j * B) * TS] = uq[q];
+                    }
+                }
+            }
+        } else {
+            for (int j = pe + e0; j <= nf; j += TE) {
+                double* colj = Fl + j * colstride;
+                for (int q = p0; q < pe - 1; ++q) {
+                    const double uq = colj[q * TS];
+                    const double* lq = Fl + q * colstride;
+                    for (int r = q + 1; r < pe; ++r) colj[r * TS] -= lq[r * TS] * uq;
+                }
             }
         }
         __syncthreads();
-        const int pb = pe - p0;
         for (int i = pe + er; i < nf; i += TR) {
             double* rowi = Fl + i * TS;
             double l[B];
 #pragma unroll
-            for (int q = 0; q < B; ++q) l[q] = (q < pb) ? rowi[(p0 + q) * colstride] : 0.0;
-            if (pb == B) {
-                for (int j = pe + ec; j <= nf; j += TC) {
-                    const double* uj = Fl + (p0 + j * nf) * TS;
-                    double acc = rowi[j * colstride];
+            for (int q = 0; q < B; ++q) l[q] = (q < pb) ? pan[(i + q * nf) * TS] : 0.0;
+            for (int j = pe + ec; j <= nf; j += TC) {
+                const double* uj;
+                int ust;
+                if constexpr (GLOBAL_F) { uj = Ul + j * B * TS; ust = TS; }
+                else { uj = Fl + (p0 + j * nf) * TS; ust = TS; }
+                double acc = rowi[j * colstride];
 #pragma unroll
-                    for (int q = 0; q < B; ++q) acc -= l[q] * uj[q * TS];
-                    rowi[j * colstride] = acc;
-                }
-            } else {
-                for (int j = pe + ec; j <= nf; j += TC) {
-                    const double* uj = Fl + (p0 + j * nf) * TS;
-                    double acc = rowi[j * colstride];
-                    for (int q = 0; q < pb; ++q) acc -= l[q] * uj[q * TS];
-                    rowi[j * colstride] = acc;
-                }
+                for (int q = 0; q < B; ++q)
+                    if (q < pb) acc -= l[q] * uj[q * ust];     // static register index, predicate hoisted
+                rowi[j * colstride] = acc;
             }
         }
         __syncthreads();
@@ -462,6 +501,7 @@ int bulk_lanes_for(int maxnf) { return maxnf <= 12 ? 4 : 8; }
 template <int TS>
 void set_factor_smem_attr() {
     JGB_CUDA(cudaFuncSetAttribute(mf_factor_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JGB_CUDA(cudaFuncSetAttribute(mf_factor_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
 // Backward substitution, S == 1: one CTA per front, pivots processed in blocks of 32 rows from the bottom up.
@@ -724,7 +764,8 @@ void MfSolver::plan(int S) {
             int trw = 1;
             while (trw < nf && trw < te) trw *= 2;     // rows first: one lane per front row when the lanes allow
             fl.tr = std::min(pow2_floor(te), trw);
-            if (!fl.bulk && !fl.colreg) fl.smem = fl.global_front ? 0 : per * fl.ts;
+            if (!fl.bulk && !fl.colreg)
+                fl.smem = fl.global_front ? (size_t)(nf * 8 + 8 * (nf + 1)) * fl.ts * sizeof(double) : per * fl.ts;
             fl.gstride = (long long)nf * (nf + 1) * fl.ts;
             if (fl.global_front)
                 gwork_need = std::max<size_t>(gwork_need, (size_t)fl.gstride * fl.count * (S / fl.ts));
@@ -809,7 +850,7 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
             launch_factor_col(fl.colreg, grid, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p, d_upd.p,
                               S, active, status);
         else if (fl.global_front)
-            launch_factor<true>(fl.ts, grid, fl.threads, 0, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
+            launch_factor<true>(fl.ts, grid, fl.threads, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
                                 d_upd.p, S, fl.tr, active, status, d_gwork.p, fl.gstride);
         else
             launch_factor<false>(fl.ts, grid, fl.threads, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs,

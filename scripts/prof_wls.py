@@ -1,0 +1,16 @@
+"""Profiling driver for the WLS path (run under ncu): single-case stateEstimation!"""
+import sys
+import numpy as np
+sys.path.insert(0, '.')
+import jgb200
+ps = jgb200.synthetic_grid()
+ctx = jgb200.Context(0)
+a = jgb200.newton_raphson(ps, ctx); jgb200.power_flow(a)
+pw = jgb200.power(ps, a.voltage.magnitude, a.voltage.angle)
+mon = jgb200.measurement(ps)
+jgb200.add_voltmeter(mon, a.voltage.magnitude); jgb200.add_wattmeter(mon, pw); jgb200.add_varmeter(mon, pw)
+buses = np.sort(np.random.default_rng(7).choice(ps.n, ps.n // 10, replace=False))
+jgb200.add_pmu(mon, pw, a.voltage.magnitude, a.voltage.angle, buses=buses, polar=False)
+se = jgb200.gauss_newton(mon, ctx)
+print("increment", jgb200.increment(se))
+print("increment", jgb200.increment(se))
