@@ -78,18 +78,27 @@ class ClockSampler(threading.Thread):
 
 
 # --------------------------------------------------------------------------------------------- CPU reference arm
-def _cpu_worker(args):
-    """One process = one core: NR power flows for a slice of outage scenarios with the CPU restatement."""
-    ks, deadline = args
+_CPU = {}
+
+
+def _cpu_init():
+    """Per-process setup (not timed, like the GPU arm's setup): grid, Ybus, index maps, SuperLU-backed NR object."""
     import oracle
     from oracle import nr as onr
     from oracle.fast import FastNR
-    from oracle.model import apply_outage
     s = oracle.synthetic_grid()
     base = oracle.ac_model(s)
     a = onr.newton_raphson(s, base)
-    f = FastNR(a, FastNR.NOPIVOT)
-    iters = scen = 0
+    _CPU.update(s=s, base=base, f=FastNR(a, FastNR.NOPIVOT))
+
+
+def _cpu_worker(ks):
+    """One process = one core: full NR power flows for a slice of outage scenarios with the CPU restatement."""
+    from oracle.model import apply_outage
+    if not _CPU:
+        _cpu_init()
+    s, base, f = _CPU["s"], _CPU["base"], _CPU["f"]
+    iters = 0
     t0 = time.perf_counter()
     for k in ks:
         m = apply_outage(s, base, int(k))
@@ -97,28 +106,33 @@ def _cpu_worker(args):
         f.reset()
         f.power_flow(MAX_ITER, TOL)
         iters += f.iteration
-        scen += 1
-        if time.perf_counter() - t0 > deadline:
-            break
-    return iters, scen, time.perf_counter() - t0
+    return iters, len(ks), time.perf_counter() - t0
 
 
-def cpu_rate(ks, cores, seconds):
-    """NR iterations/s of the CPU restatement (C assembly loops + SuperLU, no-pivot symmetric settings = the faster
-    of the two BASELINE.md §3 settings) on `cores` processes, bounded to about `seconds` of wall time."""
-    import multiprocessing as mp
-    chunks = [ks[i::cores] for i in range(cores)]
-    t0 = time.perf_counter()
-    if cores == 1:
-        res = [_cpu_worker((chunks[0], seconds))]
-    else:
-        with mp.get_context("spawn").Pool(cores) as pool:
-            res = pool.map(_cpu_worker, [(c, seconds) for c in chunks])
-    wall = time.perf_counter() - t0
-    iters = sum(r[0] for r in res)
-    scen = sum(r[1] for r in res)
-    busy = max(r[2] for r in res)
-    return iters / busy, iters, scen, busy, wall
+class CpuArm:
+    """CPU restatement (C assembly loops + SuperLU with the no-pivot symmetric settings = the faster of the two
+    BASELINE.md §3 settings) on `cores` worker processes; only the solve loops are timed."""
+
+    def __init__(self, cores):
+        import multiprocessing as mp
+        self.cores = cores
+        self.pool = mp.get_context("spawn").Pool(cores, initializer=_cpu_init) if cores > 1 else None
+        if self.pool:
+            self.pool.map(_cpu_worker, [[] for _ in range(cores)])     # make sure every worker finished its setup
+        else:
+            _cpu_init()
+
+    def run(self, ks):
+        chunks = [ks[i::self.cores] for i in range(self.cores)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_worker, chunks) if self.pool else [_cpu_worker(chunks[0])]
+        wall = time.perf_counter() - t0
+        return sum(r[0] for r in res), sum(r[1] for r in res), wall
+
+    def close(self):
+        if self.pool:
+            self.pool.close()
+            self.pool.join()
 
 
 def run_reference(args):
@@ -129,16 +143,17 @@ def run_reference(args):
     ps = jgb200.synthetic_grid()
     elig = jgb200.eligible_outages(ps)
     cores = os.cpu_count() or 1
-    per_step = max(cores, 2 * cores)           # bounded sample: 2 scenarios per core per step
-    t_all, iters_all, scen_all = [], 0, 0
+    per_step = 4 * cores                        # bounded sample: 4 scenarios per core per step (~1 s per step)
+    arm = CpuArm(cores)
+    total, iters_all, scen_all = 0.0, 0, 0
     for step in range(args.warmup + args.steps):
-        ks = elig[(step * per_step) % 4096: (step * per_step) % 4096 + per_step]
-        rate, iters, scen, busy, wall = cpu_rate(ks, cores, 60.0)
+        lo = (step * per_step) % 4096
+        iters, scen, wall = arm.run(elig[lo: lo + per_step])
         if step >= args.warmup:
-            t_all.append(wall)
+            total += wall
             iters_all += iters
             scen_all += scen
-    total = sum(t_all)
+    arm.close()
     value = iters_all / total
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -365,7 +380,9 @@ def run_ours(args):
                 "share_of_step": {"factor": t_fac / ms_dev, "backsolve": t_bs / ms_dev, "assemble": t_asm / ms_dev}}
 
     # ---- CPU baseline: bounded sample of the same sweep on one host core (the reference is single-threaded)
-    rate, it_cpu, sc_cpu, busy, _ = cpu_rate(elig[:64], 1, 15.0)
+    arm = CpuArm(1)
+    it_cpu, sc_cpu, busy = arm.run(elig[:96])
+    rate = it_cpu / busy
     cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
            "sample": f"first {sc_cpu} outage scenarios of the sweep ({it_cpu} NR iterations, {busy:.1f} s) on 1 core; "
                      "CPU restatement of JuliaGrid: C assembly loops + SciPy SuperLU (MMD_AT_PLUS_A, no pivoting) "
@@ -393,7 +410,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scenarios", type=int, default=1024, help="outage scenarios per GPU per step")
+    ap.add_argument("--scenarios", type=int, default=4096, help="outage scenarios per GPU per step")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
