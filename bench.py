@@ -194,8 +194,9 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     S = args.scenarios
-    stream = torch.cuda.current_stream().cuda_stream
-    ctx = jgb200.Context(local, stream)
+    side = torch.cuda.Stream(device=dev)          # library work and torch CUDA events share this stream
+    torch.cuda.set_stream(side)
+    ctx = jgb200.Context(local, side.cuda_stream)
     lib = ctx.lib
 
     ps = jgb200.synthetic_grid()
@@ -352,6 +353,19 @@ def run_ours(args):
             single["wls_single_case_gn_iterations_per_s"] = it_sum / (time.perf_counter() - t0)
             single["wls_single_case_iterations"] = se.method.iteration
             single["wls_rows"] = int(t.m)
+            # configs[4]-style Monte-Carlo batch: 256 noise draws of the same measurement set on this GPU
+            Sm = 256
+            Z = np.stack([t.mean + np.sqrt(1 / wd) * np.random.default_rng(1000 + q).standard_normal(t.m)
+                          for q in range(Sm)])
+            jgb200.set_voltage_se(se, ps.vm, ps.va)
+            jgb200.wls_batch(se, Z)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rb = jgb200.wls_batch(se, Z)
+            torch.cuda.synchronize()
+            single["wls_monte_carlo_gn_iterations_per_s"] = rb.total_iterations / (time.perf_counter() - t0)
+            single["wls_monte_carlo_draws"] = Sm
+            single["wls_monte_carlo_all_converged"] = bool((rb.status == 0).all())
         except Exception as e:      # the WLS extras must never sink the headline line
             single["wls_error"] = str(e)
 

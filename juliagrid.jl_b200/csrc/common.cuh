@@ -123,6 +123,35 @@ struct PhaseTimer {
     }
     void reset() { for (int i = 0; i < 8; ++i) { ms[i] = 0; count[i] = 0; } spans.clear(); used = 0; }
 };
+// One captured + instantiated CUDA graph, rebuilt when its key (scalar kernel arguments baked in) changes.
+struct GraphSlot {
+    cudaGraphExec_t exec = nullptr;
+    double key_a = 0;
+    long long key_b = -1;
+    ~GraphSlot() { if (exec) cudaGraphExecDestroy(exec); }
+    bool valid(double a, long long b) const { return exec && key_a == a && key_b == b; }
+    template <typename F>
+    void capture(cudaStream_t st, double a, long long b, F&& enqueue) {
+        if (exec) { cudaGraphExecDestroy(exec); exec = nullptr; }
+        cudaGraph_t g = nullptr;
+        JGB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+        try {
+            enqueue();
+        } catch (...) {
+            cudaStreamEndCapture(st, &g);
+            if (g) cudaGraphDestroy(g);
+            throw;
+        }
+        JGB_CUDA(cudaStreamEndCapture(st, &g));
+        cudaError_t e = cudaGraphInstantiate(&exec, g, 0);
+        cudaGraphDestroy(g);
+        if (e != cudaSuccess) { exec = nullptr; throw CudaError(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); }
+        key_a = a;
+        key_b = b;
+    }
+    void launch(cudaStream_t st) { JGB_CUDA(cudaGraphLaunch(exec, st)); }
+};
+
 enum Phase { kPhAssemble = 0, kPhFactor = 1, kPhBacksolve = 2, kPhUpdate = 3, kPhGain = 4, kPhRows = 5 };
 
 }  // namespace jgb

@@ -433,31 +433,53 @@ int NrContext::run(int64_t max_iter, double tol, int64_t* iters, double* sp, dou
     JGB_CUDA(cudaMemcpyAsync(d_status.p, &one, sizeof(int), cudaMemcpyHostToDevice, stream));
     iteration = 0;
     int rc = 1;
-    for (int64_t it = 0; it <= max_iter; ++it) {
+    const int per_solve = solver.launches_per_solve(1);      // also plans / allocates before any capture
+    // mismatch! + convergence bookkeeping + the 16-byte read-back: the head of every loop trip
+    auto enqueue_head = [&] {
         JGB_CUDA(cudaMemsetAsync(d_remaining.p, 0, sizeof(int), stream));
-        launch_assemble(1, false);
+        dim3 block(1, 128);
+        nr_assemble_kernel<<<dim3(ceil_div(n, 128), 1), block, 0, stream>>>(d, 1, 128, kWriteF | kWriteJ);
         nr_check_kernel<<<1, 32, 0, stream>>>(d, 1, 1, tol, (int)max_iter);
-        ++launches;
         JGB_CUDA(cudaMemcpyAsync(h_int.p, d_remaining.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         JGB_CUDA(cudaMemcpyAsync(h_int.p + 1, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        d_stop.download(h_stop.p, 2, stream);
+        JGB_CUDA(cudaMemcpyAsync(h_stop.p, d_stop.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    };
+    // solve! (refactor + solve + update) followed by the next head
+    auto enqueue_iter = [&] {
+        solver.factor_solve(d_jval.p, d_f.p, d_inc.p, 1, d_active.p, d_status.p, stream);
+        nr_update_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(d, 1);
+        enqueue_head();
+    };
+    const bool use_graph = !timer.enabled && !graphs_disabled;
+    if (use_graph) {
+        if (!graph_head.valid(tol, max_iter)) graph_head.capture(stream, tol, max_iter, enqueue_head);
+        if (!graph_iter.valid(tol, max_iter)) graph_iter.capture(stream, tol, max_iter, enqueue_iter);
+    }
+    if (use_graph) graph_head.launch(stream); else enqueue_head();
+    launches += 2;
+    for (int64_t it = 0; it <= max_iter; ++it) {
         JGB_CUDA(cudaStreamSynchronize(stream));
         timer.resolve();
         if (h_int.p[0] == 0) { rc = h_int.p[1]; break; }
-        timer.mark(stream);
-        const size_t f0 = timer.last();
-        cudaEvent_t mid = timer.reserve();
-        const size_t f1 = timer.last();
-        solver.factor_solve(d_jval.p, d_f.p, d_inc.p, 1, d_active.p, d_status.p, stream, mid);
-        launches += solver.launches_per_solve(1);
-        timer.mark(stream);
-        const size_t f2 = timer.last();
-        timer.span(kPhFactor, f0, f1);
-        timer.span(kPhBacksolve, f1, f2);
-        nr_update_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(d, 1);
-        ++launches;
+        if (use_graph) {
+            graph_iter.launch(stream);
+        } else {
+            timer.mark(stream);
+            const size_t f0 = timer.last();
+            cudaEvent_t mid = timer.reserve();
+            const size_t f1 = timer.last();
+            solver.factor_solve(d_jval.p, d_f.p, d_inc.p, 1, d_active.p, d_status.p, stream, mid);
+            timer.mark(stream);
+            const size_t f2 = timer.last();
+            timer.span(kPhFactor, f0, f1);
+            timer.span(kPhBacksolve, f1, f2);
+            nr_update_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(d, 1);
+            enqueue_head();
+        }
+        launches += per_solve + 3;
         iteration += 1;
     }
+    JGB_CUDA(cudaGetLastError());
     jac_valid = true;
     if (iters) *iters = iteration;
     if (sp) *sp = h_stop.p[0];

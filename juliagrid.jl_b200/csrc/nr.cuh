@@ -2,6 +2,7 @@
 // per-iteration kernels. Stands in for src/powerFlow/acPowerFlow.jl:39-175 (setup), :645-685 (mismatch!),
 // :793-911 (solve!), :1389-1433 (powerFlow! loop) of the reference.
 #pragma once
+#include <cstdlib>
 #include "common.cuh"
 #include "solver.cuh"
 
@@ -59,6 +60,7 @@ class NrContext {
     std::vector<int64_t> pq1, pvpq1, pcount1, jcolptr1, jrowval1;
     long long launches = 0;
     PhaseTimer timer;
+    GraphSlot graph_head, graph_iter;   // single-case powerFlow! loop as two CUDA graphs
 
   private:
     void alloc_state(int S);
@@ -89,6 +91,7 @@ class NrContext {
     PinnedBuf<double> h_stop;
     PinnedBuf<int> h_int;
     int64_t iteration = 0;
+    bool graphs_disabled = getenv("JGB_NO_GRAPH") != nullptr;
     bool jac_valid = false;
     bool have_injection = false, have_state = false;
 };
