@@ -201,94 +201,162 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __rest
     }
 }
 
-// ---- column-in-registers variant for mid-size fronts (batch): TE = blockDim / TS lanes per scenario, lane e owns
-// column e of the front (nf + 1 <= TE columns incl. rhs) in registers; the pivot column is broadcast through a
-// shared-memory strip, so a multiply-add costs one LDS (broadcast) + one DFMA instead of two LDS + STS + index math.
-template <int TS, int MAXNF>
+// ---- symmetric (LDL^T) variant for the WLS gain matrix --------------------------------------------------------
+// The front holds only its lower triangle, packed by columns (column j starts at j*(2nf-j+1)/2 and has nf-j entries),
+// plus the rhs vector and the scaled multipliers of the current panel, so fronts up to order 208 fit in shared memory
+// and the trailing update does half the work. Column p keeps the unscaled entries c_i = F[i,p]: they are row p of
+// U = D L^T, so the packed-U output and the back-solve kernels are shared with the LU path. The update block is written
+// in full (upper part mirrored) so any kind of parent kernel can consume it.
+constexpr int kMaxSymFront = 208;
+
+__device__ __forceinline__ int sym_col(int j, int nf) { return (j * (2 * nf - j + 1)) >> 1; }
+
+template <int TS>
 __global__ void __launch_bounds__(256)
-mf_factor_col_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ aval,
-                     const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S,
+mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ aval,
+                     const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S, int TR,
                      const unsigned char* __restrict__ active, int* __restrict__ status) {
     extern __shared__ double Fs[];
-    const int sl = threadIdx.x % TS, e0 = threadIdx.x / TS;
-    constexpr int TE = 256 / TS;
-    static_assert(TE >= MAXNF + 1, "one lane per column");
+    const int sl = threadIdx.x % TS;
     double* Fl = Fs + sl;
     const int f = fronts[blockIdx.x];
+    const int e0 = threadIdx.x / TS;
+    const int TE = blockDim.x / TS;
+    const int er = e0 % TR, ec = e0 / TR, TC = TE / TR;
     const int s = blockIdx.y * TS + sl;
     const bool act = active ? (active[s] != 0) : true;
     if (!__syncthreads_or(act)) return;
     const int nf = sy.f_nf[f], k = sy.f_k[f], u = nf - k;
     const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
-    const int total = nf * (nf + 1);
-    for (int pos = e0; pos < total; pos += TE) Fl[pos * TS] = 0.0;
+    const int tri = (nf * (nf + 1)) >> 1;
+    double* Rl = Fl + tri * TS;                 // rhs: element i at Rl[i * TS]
+    double* Lp = Fl + (tri + nf) * TS;          // panel multipliers: element (i, q) at Lp[(i + q*nf) * TS]
+    constexpr int B = 8;
+    for (int pos = e0; pos < tri + nf; pos += TE) Fl[pos * TS] = 0.0;
     __syncthreads();
     if (act) {
         const double* __restrict__ av = aval + s;
         const int a1 = sy.f_asmptr[f + 1];
-        for (int a = sy.f_asmptr[f] + e0; a < a1; a += TE) Fl[sy.asm_dst[a] * TS] = av[(long long)sy.asm_src[a] * S];
-        for (int p = e0; p < k; p += TE) Fl[(p + nf * nf) * TS] = rhs[(long long)rows[p] * S + s];
+        for (int a = sy.f_asmptr[f] + e0; a < a1; a += TE) {
+            const int dst = sy.asm_dst[a];
+            const int c = dst / nf, r = dst - c * nf;
+            if (r >= c) Fl[(sym_col(c, nf) + r - c) * TS] = av[(long long)sy.asm_src[a] * S];
+        }
+        for (int p = e0; p < k; p += TE) Rl[p * TS] = rhs[(long long)rows[p] * S + s];
     }
     __syncthreads();
     const int W = S < 32 ? S : 32;
     double* __restrict__ up = upd + (long long)(s / W) * sy.upd_size * W + (s % W);
     {
         const int r1 = sy.f_eaptr[f + 1];
-        for (int r = sy.f_eaptr[f]; r < r1; ++r) {      // rounds: distinct destinations inside a round
-            const int t1 = sy.ea_roundptr[r + 1];
+        for (int rd = sy.f_eaptr[f]; rd < r1; ++rd) {
+            const int t1 = sy.ea_roundptr[rd + 1];
             if (act) {
 #pragma unroll 4
-                for (int t = sy.ea_roundptr[r] + e0; t < t1; t += TE) {
+                for (int t = sy.ea_roundptr[rd] + e0; t < t1; t += TE) {
                     const int2 pr = sy.ea_pair[t];
-                    Fl[pr.x * TS] += up[(long long)pr.y * W];
+                    const int c = pr.x / nf, r = pr.x - c * nf;
+                    if (c == nf) Rl[r * TS] += up[(long long)pr.y * W];
+                    else if (r >= c) Fl[(sym_col(c, nf) + r - c) * TS] += up[(long long)pr.y * W];
                 }
             }
             __syncthreads();
         }
     }
-    const int c = e0;                        // my column
-    const bool mine = c <= nf;
-    double col[MAXNF];
-#pragma unroll
-    for (int i = 0; i < MAXNF; ++i) col[i] = (mine && i < nf) ? Fl[(i + c * nf) * TS] : 0.0;
-    __syncthreads();                         // the front area is reused as the broadcast strip from here on
-    double* bc = Fs + sl;                    // 2 x MAXNF x TS doubles
-    double cur = col[0];                     // col[p] of the running pivot row
     bool bad = false;
-    double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
-    for (int p = 0; p < k; ++p) {
-        double* b = bc + (p & 1) * (MAXNF * TS);
-        if (c == p) {
-#pragma unroll
-            for (int i = 0; i < MAXNF; ++i)
-                if (i >= p && i < nf) b[i * TS] = col[i];
+    for (int p0 = 0; p0 < k; p0 += B) {
+        const int pe = (p0 + B < k) ? p0 + B : k;
+        const int pb = pe - p0;
+        for (int p = p0; p < pe; ++p) {
+            const double* colp = Fl + (sym_col(p, nf) - p) * TS;      // element (i, p) at colp[i * TS]
+            const double piv = colp[p * TS];
+            if (piv == 0.0 || !isfinite(piv)) bad = true;
+            const double inv = 1.0 / piv;
+            for (int i = p + 1 + e0; i < nf; i += TE) {
+                const double li = colp[i * TS] * inv;
+                Lp[(i + (p - p0) * nf) * TS] = li;
+                const int jend = (i + 1 < pe) ? i + 1 : pe;
+                for (int j = p + 1; j < jend; ++j) Fl[(sym_col(j, nf) + i - j) * TS] -= li * colp[j * TS];
+            }
+            __syncthreads();
         }
-        __syncthreads();
-        const double piv = b[p * TS];
-        if (piv == 0.0 || !isfinite(piv)) bad = true;
-        const double inv = 1.0 / piv;
-        if (act && mine && c >= p) Uf[(urow_off(p, nf) + (c - p)) * S] = (c == p) ? inv : cur;
-        const double m = (mine && c > p) ? inv * cur : 0.0;
-        double nxt = 0.0;
-#pragma unroll
-        for (int i0 = 0; i0 < MAXNF; i0 += 8) {
-            if (i0 + 8 <= p + 1) continue;           // whole chunk above the pivot row: nothing to do (uniform)
-#pragma unroll
-            for (int i = i0; i < i0 + 8; ++i) {
-                if (i > p) col[i] -= b[i * TS] * m;  // rows >= nf hold zeros in b? no: guard through m / zero columns
-                if (i == p + 1) nxt = col[i];
+        if (e0 == 0) {      // forward substitution of the rhs inside the block (tiny, sequential)
+            for (int q = p0; q < pe - 1; ++q) {
+                const double yq = Rl[q * TS];
+                for (int r = q + 1; r < pe; ++r) Rl[r * TS] -= Lp[(r + (q - p0) * nf) * TS] * yq;
             }
         }
-        cur = nxt;
+        __syncthreads();
+        // trailing update of the lower triangle, rows folded in pairs (t-th from the top with t-th from the bottom)
+        // so that every lane sweeps the same number of columns
+        const double* cb[B];
+#pragma unroll
+        for (int q = 0; q < B; ++q) cb[q] = Fl + (sym_col(p0 + (q < pb ? q : 0), nf) - (p0 + (q < pb ? q : 0))) * TS;
+        const int nt = nf - pe;                 // trailing rows pe .. nf-1
+        for (int t = er; 2 * t < nt; t += TR) {
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int i = half == 0 ? pe + t : nf - 1 - t;
+                if (half == 1 && i == pe + t) break;
+                double l[B];
+#pragma unroll
+                for (int q = 0; q < B; ++q) l[q] = (q < pb) ? Lp[(i + q * nf) * TS] : 0.0;
+                for (int j = pe + ec; j <= i; j += TC) {
+                    double* dstp = Fl + (sym_col(j, nf) + i - j) * TS;
+                    double acc = *dstp;
+#pragma unroll
+                    for (int q = 0; q < B; ++q) acc -= l[q] * cb[q][j * TS];   // l[q] = 0 beyond the block
+                    *dstp = acc;
+                }
+                if (ec == 0) {
+                    double acc = Rl[i * TS];
+#pragma unroll
+                    for (int q = 0; q < B; ++q)
+                        if (q < pb) acc -= l[q] * Rl[(p0 + q) * TS];
+                    Rl[i * TS] = acc;
+                }
+            }
+        }
+        __syncthreads();
     }
     if (!act) return;
     if (bad && e0 == 0) status[s] = -3;
-    if (mine && c >= k) {
-        double* Cj = up + (sy.f_updoff[f] + (long long)(c - k) * u) * W;
-#pragma unroll
-        for (int i = 0; i < MAXNF; ++i)
-            if (i >= k && i < nf) Cj[(long long)(i - k) * W] = col[i];
+    double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
+    for (int p = ec; p < k; p += TC) {
+        double* Urow = Uf + urow_off(p, nf) * S;
+        const double* colp = Fl + (sym_col(p, nf) - p) * TS;
+        for (int j = p + er; j <= nf; j += TR) {
+            const double v = (j < nf) ? colp[j * TS] : Rl[p * TS];
+            Urow[(long long)(j - p) * S] = (j == p) ? 1.0 / v : v;
+        }
     }
+    double* __restrict__ Cf = up + sy.f_updoff[f] * W;
+    for (int j = ec; j <= u; j += TC) {
+        double* Cj = Cf + (long long)j * u * W;
+        for (int i = er; i < u; i += TR) {
+            double v;
+            if (j == u) v = Rl[(k + i) * TS];
+            else {
+                const int r = i >= j ? i : j, c = i >= j ? j : i;
+                v = Fl[(sym_col(k + c, nf) + r - c) * TS];
+            }
+            Cj[(long long)i * W] = v;
+        }
+    }
+}
+
+void launch_factor_sym(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st, DevSym dev, const int* fronts,
+                       const double* aval, const double* rhs, double* U, double* upd, int S, int tr,
+                       const unsigned char* active, int* status) {
+#define JGB_CASE(T)                                                                                                \
+    case T:                                                                                                        \
+        mf_factor_sym_kernel<T><<<grid, threads, smem, st>>>(dev, fronts, aval, rhs, U, upd, S, tr, active, status); \
+        break;
+    switch (ts) {
+        JGB_CASE(1) JGB_CASE(2) JGB_CASE(4) JGB_CASE(8) JGB_CASE(16) JGB_CASE(32)
+        default: throw std::runtime_error("unsupported scenario tile");
+    }
+#undef JGB_CASE
 }
 
 // ---- TMA-staged variant for the many small fronts of a batch -------------------------------------------------
@@ -481,17 +549,6 @@ void launch_factor(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st,
 #undef JGB_CASE
 }
 
-void launch_factor_col(int maxnf, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const int* fronts,
-                       const double* aval, const double* rhs, double* U, double* upd, int S,
-                       const unsigned char* active, int* status) {
-    if (maxnf == 31)
-        mf_factor_col_kernel<8, 31><<<grid, 256, smem, st>>>(dev, fronts, aval, rhs, U, upd, S, active, status);
-    else if (maxnf == 63)
-        mf_factor_col_kernel<4, 63><<<grid, 256, smem, st>>>(dev, fronts, aval, rhs, U, upd, S, active, status);
-    else
-        throw std::runtime_error("unsupported column-register factor variant");
-}
-
 // (lanes per scenario, register bound on the front order) variants of the bulk kernel
 #define JGB_BULK_VARIANTS(X) X(4, 8) X(4, 12) X(8, 16) X(8, 20)
 
@@ -516,6 +573,7 @@ template <int TS>
 void set_factor_smem_attr() {
     JGB_CUDA(cudaFuncSetAttribute(mf_factor_kernel<TS, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     JGB_CUDA(cudaFuncSetAttribute(mf_factor_kernel<TS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    JGB_CUDA(cudaFuncSetAttribute(mf_factor_sym_kernel<TS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
 // Backward substitution, S == 1: one CTA per front, pivots processed in blocks of 32 rows from the bottom up.
@@ -633,8 +691,9 @@ int pow2_floor(int v) {
 
 }  // namespace
 
-void MfSolver::setup(const Symbolic& s, cudaStream_t st) {
+void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) {
     sym = s;
+    symmetric = symmetric_matrix;
     d_f_k.upload(sym.f_k, st);
     d_f_nf.upload(sym.f_nf, st);
     d_f_rowptr.upload(sym.f_rowptr, st);
@@ -670,8 +729,6 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st) {
     JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_tile_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    JGB_CUDA(cudaFuncSetAttribute(mf_factor_col_kernel<8, 31>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    JGB_CUDA(cudaFuncSetAttribute(mf_factor_col_kernel<4, 63>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 #define X(TE, MAXNF) \
     JGB_CUDA(cudaFuncSetAttribute(mf_factor_bulk_kernel<TE, MAXNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     JGB_BULK_VARIANTS(X)
@@ -709,14 +766,13 @@ void MfSolver::plan(int S) {
     // factor launch classes: fronts of a level are sorted by decreasing order and cut at these bounds
     // single case: one launch per level (launch latency dominates; measured 625 us vs 855 us per factorisation with
     // four size classes on the 10k-bus Jacobian)
-    static const std::vector<PlanRule> single_rules = {{kMaxSmemFront, 1, 256}};
+    static const std::vector<PlanRule> single_rules = {{kMaxSmemFront, 1, 256}, {kMaxSymFront, 1, 256}};
     static const std::vector<PlanRule> batch_rules = {{8, 32, 128}, {12, 32, 128}, {16, 32, 256}, {20, 32, 256},
                                                       {24, 8, 256}, {32, 8, 256}, {48, 4, 256}, {64, 2, 256},
-                                                      {96, 1, 256}, {kMaxSmemFront, 1, 256}};
+                                                      {96, 1, 256}, {kMaxSmemFront, 1, 256},
+                                                      {kMaxSymFront, 1, 256}};
     const char* nb = getenv("JGB_NO_BULK");
     const bool bulk_enabled = !(nb && *nb == '1');
-    const char* nc = getenv("JGB_COLREG");     // experimental column-in-registers kernel: off unless JGB_COLREG=1
-    const bool colreg_enabled = (nc && *nc == '1');
     const std::vector<PlanRule> rules = (S == 1) ? parse_rules("JGB_FPLAN_SINGLE", single_rules)
                                                  : parse_rules("JGB_FPLAN_BATCH", batch_rules);
     auto cls = [&](int nf) { size_t c = 0; while (c < rules.size() && nf > rules[c].maxnf) ++c; return (int)c; };
@@ -732,7 +788,8 @@ void MfSolver::plan(int S) {
             FactorLaunch fl{};
             fl.begin = i;
             fl.count = j - i;
-            fl.global_front = nf > kMaxSmemFront || c >= (int)rules.size();
+            fl.sym = symmetric && nf <= kMaxSymFront;
+            fl.global_front = !fl.sym && (nf > kMaxSmemFront || c >= (int)rules.size());
             fl.bulk = false;
             if (!fl.global_front && S >= 32 && bulk_enabled && bulk_variant_for(nf) != 0) {
                 fl.maxnf = bulk_variant_for(nf);
@@ -759,28 +816,30 @@ void MfSolver::plan(int S) {
                     fl.smem = bytes;
                 }
             }
-            fl.colreg = 0;
-            if (!fl.bulk && !fl.global_front && S >= 32 && colreg_enabled && nf <= 63) {
-                fl.colreg = rules[c].maxnf <= 32 ? 31 : 63;
-                if (nf > fl.colreg) fl.colreg = 63;
-                fl.ts = fl.colreg == 31 ? 8 : 4;
-                fl.threads = 256;
-                fl.smem = std::max(per * fl.ts, (size_t)2 * (fl.colreg + 1) * fl.ts * sizeof(double));
-            }
-            if (fl.bulk || fl.colreg) {
+            if (fl.bulk) {
             } else if (fl.global_front) {
                 fl.ts = (S == 1) ? 1 : 4;
                 fl.threads = 256;
             } else {
-                fl.ts = std::min(rules[c].ts, S);
-                fl.threads = std::max(rules[c].threads, fl.ts);
+                const PlanRule& rl = rules[std::min<size_t>(c, rules.size() - 1)];
+                fl.ts = std::min(rl.ts, S);
+                fl.threads = std::max(rl.threads, fl.ts);
                 while (fl.ts > 1 && per * fl.ts > 200 * 1024) fl.ts /= 2;
             }
             int te = fl.threads / fl.ts;
             int trw = 1;
             while (trw < nf && trw < te) trw *= 2;     // rows first: one lane per front row when the lanes allow
             fl.tr = std::min(pow2_floor(te), trw);
-            if (!fl.bulk && !fl.colreg)
+            if (fl.bulk) fl.sym = false;
+            if (fl.sym) {
+                const size_t sper = ((size_t)nf * (nf + 1) / 2 + nf + (size_t)nf * 8) * sizeof(double);
+                if (c >= (int)rules.size()) { fl.ts = 1; fl.threads = 256; }
+                while (fl.ts > 1 && sper * fl.ts > 200 * 1024) fl.ts /= 2;
+                fl.smem = sper * fl.ts;
+                int te2 = fl.threads / fl.ts, trw2 = 1;
+                while (trw2 < (nf + 1) / 2 && trw2 < te2) trw2 *= 2;      // folded rows: nf/2 row pairs
+                fl.tr = std::min(pow2_floor(te2), trw2);
+            } else if (!fl.bulk)
                 fl.smem = fl.global_front ? (size_t)(nf * 8 + 8 * (nf + 1)) * fl.ts * sizeof(double) : per * fl.ts;
             fl.gstride = (long long)nf * (nf + 1) * fl.ts;
             if (fl.global_front)
@@ -862,12 +921,12 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
         if (fl.bulk)
             launch_factor_bulk(fl.maxnf, grid, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
                                d_upd.p, S, fl.smem_elems, active, status);
-        else if (fl.colreg)
-            launch_factor_col(fl.colreg, grid, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p, d_upd.p,
-                              S, active, status);
         else if (fl.global_front)
             launch_factor<true>(fl.ts, grid, fl.threads, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
                                 d_upd.p, S, fl.tr, active, status, d_gwork.p, fl.gstride);
+        else if (fl.sym)
+            launch_factor_sym(fl.ts, grid, fl.threads, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
+                              d_upd.p, S, fl.tr, active, status);
         else
             launch_factor<false>(fl.ts, grid, fl.threads, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs,
                                  d_U.p, d_upd.p, S, fl.tr, active, status, nullptr, 0);

@@ -26,7 +26,7 @@ struct FactorLaunch {
     size_t smem;
     bool global_front;     // front kept in a global workspace instead of shared memory
     bool bulk;             // TMA-staged small-front kernel (batch only)
-    int colreg;            // column-in-registers kernel variant (0 = not used)
+    bool sym;              // packed symmetric (LDL^T) kernel
     int maxnf;             // bulk: register bound on the front order (kernel variant)
     int smem_elems;        // bulk: front + staging capacity in elements (x 32 lanes x 8 bytes)
     long long gstride;
@@ -43,7 +43,8 @@ class MfSolver {
   public:
     Symbolic sym;
 
-    void setup(const Symbolic& s, cudaStream_t st);
+    // symmetric_matrix: the values are symmetric (WLS gain): mid-size fronts use the LDL^T variant of the kernel
+    void setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix = false);
     // Factor A (values `aval`, CSC order of the analysed pattern, [nnz][S]) and solve A x = rhs for every scenario.
     // `active` (nullable, [S]) skips scenarios whose flag is 0. `status[s]` is set to -3 on a zero / non-finite pivot.
     void factor_solve(const double* aval, const double* rhs, double* x, int S, const unsigned char* active,
@@ -55,6 +56,7 @@ class MfSolver {
   private:
     void plan(int S);
     int planned_S = -1;
+    bool symmetric = false;
     std::vector<FactorLaunch> fplan;
     std::vector<SolveLaunch> splan;
     DevBuf<int> d_f_k, d_f_nf, d_f_rowptr, d_f_rows, d_f_relptr, d_f_rel, d_f_childptr, d_f_children, d_f_asmptr,

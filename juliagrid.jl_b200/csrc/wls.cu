@@ -606,10 +606,10 @@ void WlsContext::setup(int64_t n_, int64_t m_, int64_t slack_, const int64_t* hc
     {
         Symbolic sym;
         analyse(nv, gcolptr.data(), grow.data(), group.data(), nullptr, latency_options(), sym);
-        solver.setup(sym, stream);
+        solver.setup(sym, stream, true);
         Symbolic symb;
         analyse(nv, gcolptr.data(), grow.data(), group.data(), nullptr, throughput_options(), symb);
-        solver_batch.setup(symb, stream);
+        solver_batch.setup(symb, stream, true);
     }
     // ---- branch coefficients
     std::vector<double> bg(nbr), bb(nbr), bgsi(nbr), bbsi(nbr), btinv(nbr), bphi(nbr);
