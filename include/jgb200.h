@@ -80,6 +80,20 @@ int32_t jgb_nr_batch_dev(jgb_ctx* ctx, int64_t S, const int64_t* out_from_dev, c
                          const double* dy_dev, int64_t max_iter, double tol, double* vm_out_dev, double* va_out_dev,
                          int32_t* iterations_dev, int8_t* status_dev, int64_t* total_iterations);
 
+/* ---- post-processing on the device ------------------------------------------------------ */
+/* branch.layout.from/to (1-based), model.ac.nodalFromFrom / nodalFromTo / nodalToFrom / nodalToTo (ComplexF64) and
+ * branch.layout.status, needed by jgb_nr_power only */
+int32_t jgb_nr_set_branches(jgb_ctx* ctx, int64_t nbranch, const int64_t* from, const int64_t* to,
+                            const double* y_ff_re_im, const double* y_ft_re_im, const double* y_tf_re_im,
+                            const double* y_tt_re_im, const int8_t* status);
+/* power!(analysis) / current!(analysis) for the quantities the measurement generators consume
+ * (postprocessing/acAnalysis.jl:30-79, 672-700), evaluated at the state on the device: bus injections (n) and, per
+ * branch, from/to active and reactive flows and current magnitude / angle (out-of-service branches give 0).
+ * Any pointer may be NULL. */
+int32_t jgb_nr_power(jgb_ctx* ctx, double* injection_active, double* injection_reactive, double* from_active,
+                     double* from_reactive, double* to_active, double* to_reactive, double* from_current_magnitude,
+                     double* from_current_angle, double* to_current_magnitude, double* to_current_angle);
+
 /* ---- Gauss-Newton WLS AC state estimation ---------------------------------------------------------------------- */
 /* gaussNewton(monitoring) after acWLS (acStateEstimation.jl:43-259): takes the tables acWLS builds — the CSC pattern
  * of the Jacobian H (m x 2n; theta columns 1..n, V columns n+1..2n), type (Int8 codes 0..21), index (bus or branch),

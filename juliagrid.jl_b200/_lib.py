@@ -39,6 +39,8 @@ PROTOTYPES = {
     "jgb_nr_solve": (C.c_int32, [C.c_void_p]),
     "jgb_nr_get_vectors": (C.c_int32, [C.c_void_p, c_f64p, c_f64p, c_f64p, c_i64p]),
     "jgb_nr_run": (C.c_int32, [C.c_void_p, C.c_int64, C.c_double, c_i64p, c_f64p, c_f64p]),
+    "jgb_nr_set_branches": (C.c_int32, [C.c_void_p, C.c_int64, c_i64p, c_i64p, c_f64p, c_f64p, c_f64p, c_f64p, c_i8p]),
+    "jgb_nr_power": (C.c_int32, [C.c_void_p] + [c_f64p] * 10),
     "jgb_nr_batch": (C.c_int32, [C.c_void_p, C.c_int64, c_i64p, c_i64p, c_f64p, C.c_int64, C.c_double, c_f64p,
                                  c_f64p, c_i32p, c_i8p, c_i64p]),
     "jgb_nr_batch_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,

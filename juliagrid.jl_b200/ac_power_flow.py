@@ -171,6 +171,27 @@ def power_flow(a: AcPowerFlow, iteration: int = 20, tolerance: float = 1e-8) -> 
     return rc == 0
 
 
+_POWER_KEYS = ("injection_active", "injection_reactive", "from_active", "from_reactive", "to_active", "to_reactive",
+               "from_current_magnitude", "from_current_angle", "to_current_magnitude", "to_current_angle")
+
+
+def power_device(a: AcPowerFlow) -> dict:
+    """power!(analysis) + current!(analysis) on the device (postprocessing/acAnalysis.jl:30-79, 672-700): bus
+    injections and branch from/to flows and currents at the analysis' present state."""
+    sysm, mdl, lib = a.system, a.system.model, a.ctx.lib
+    if a._state_dirty:
+        a._push_state()
+    if not getattr(a, "_branches_set", False):
+        a.ctx.check(lib.jgb_nr_set_branches(a.ctx.handle, sysm.nbr, ptr(i64(sysm.frm + 1), C.c_int64),
+                                            ptr(i64(sysm.to + 1), C.c_int64), ptr(cplx(mdl.y_ff), C.c_double),
+                                            ptr(cplx(mdl.y_ft), C.c_double), ptr(cplx(mdl.y_tf), C.c_double),
+                                            ptr(cplx(mdl.y_tt), C.c_double), ptr(i8(sysm.status), C.c_int8)))
+        a._branches_set = True
+    out = {k: np.empty(sysm.n if k.startswith("injection") else sysm.nbr) for k in _POWER_KEYS}
+    a.ctx.check(lib.jgb_nr_power(a.ctx.handle, *[ptr(out[k], C.c_double) for k in _POWER_KEYS]))
+    return out
+
+
 def set_initial_point(a: AcPowerFlow):
     """setInitialPoint!(analysis): back to the start point of the constructor."""
     a.voltage = Polar(a._initial[0].copy(), a._initial[1].copy())
@@ -221,6 +242,7 @@ def update_branch(a: AcPowerFlow, k: int, status: int):
     ytv = cplx(mdl.nzval_t[pos])
     a.ctx.check(a.ctx.lib.jgb_nr_update_y(a.ctx.handle, 4, ptr(p1, C.c_int64), ptr(yv, C.c_double),
                                           ptr(ytv, C.c_double)))
+    a._branches_set = False       # Y-parameters / statuses changed: re-upload before the next power_device
 
 
 # camelCase aliases matching the reference's exported names

@@ -194,6 +194,20 @@ int32_t jgb_nr_run(jgb_ctx* ctx, int64_t max_iter, double tol, int64_t* iteratio
     });
 }
 
+int32_t jgb_nr_set_branches(jgb_ctx* ctx, int64_t nbranch, const int64_t* from, const int64_t* to, const double* y_ff,
+                            const double* y_ft, const double* y_tf, const double* y_tt, const int8_t* status) {
+    return guarded(ctx, [&] { nr_of(ctx).set_branches(nbranch, from, to, y_ff, y_ft, y_tf, y_tt, status); return 0; });
+}
+
+int32_t jgb_nr_power(jgb_ctx* ctx, double* inj_p, double* inj_q, double* from_p, double* from_q, double* to_p,
+                     double* to_q, double* from_im, double* from_ia, double* to_im, double* to_ia) {
+    return guarded(ctx, [&] {
+        double* out[10] = {inj_p, inj_q, from_p, from_q, to_p, to_q, from_im, from_ia, to_im, to_ia};
+        nr_of(ctx).power(out);
+        return 0;
+    });
+}
+
 int32_t jgb_nr_batch(jgb_ctx* ctx, int64_t S, const int64_t* out_from, const int64_t* out_to, const double* dy,
                      int64_t max_iter, double tol, double* vm_out, double* va_out, int32_t* iterations,
                      int8_t* status, int64_t* total_iterations) {

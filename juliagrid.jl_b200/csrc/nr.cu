@@ -200,7 +200,101 @@ __global__ void copy_results_kernel(const int* __restrict__ iters, const int* __
     st_out[s] = (int8_t)status[s];
 }
 
+// power! / current! (postprocessing/acAnalysis.jl:30-79, 672-700): thread t < n -> bus injection
+// S_i = V_i conj(sum_j Y_ij V_j) over the Ybus strip; thread n + k -> branch k: I_from = Yff V_i + Yft V_j,
+// I_to = Ytf V_i + Ytt V_j, S = V conj(I). Output layout: [inj_p | inj_q] (n each), then 8 branch vectors (nbr each).
+__global__ void nr_power_kernel(NrDev d, int nbr, const int* __restrict__ bf, const int* __restrict__ bt,
+                                const double2* __restrict__ yff, const double2* __restrict__ yft,
+                                const double2* __restrict__ ytf, const double2* __restrict__ ytt,
+                                const signed char* __restrict__ st, double* __restrict__ out) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = d.n;
+    if (t < n) {
+        double re = 0.0, im = 0.0;
+        for (int p = d.ycolptr[t]; p < d.ycolptr[t + 1]; ++p) {
+            const int j = d.yrow[p];
+            const double2 y = d.yt[p];      // Y[t, j]
+            double sn, cs;
+            sincos(d.va[j], &sn, &cs);
+            const double vr = d.vm[j] * cs, vi = d.vm[j] * sn;
+            re += y.x * vr - y.y * vi;
+            im += y.x * vi + y.y * vr;
+        }
+        double sn, cs;
+        sincos(d.va[t], &sn, &cs);
+        const double vr = d.vm[t] * cs, vi = d.vm[t] * sn;
+        out[t] = vr * re + vi * im;          // Re(V conj(I))
+        out[n + t] = vi * re - vr * im;      // Im(V conj(I))
+    } else if (t < n + nbr) {
+        const int k = t - n;
+        double* o = out + 2 * n;
+        if (st[k] != 1) {
+            for (int q = 0; q < 8; ++q) o[(long long)q * nbr + k] = 0.0;
+            return;
+        }
+        const int i = bf[k], j = bt[k];
+        double si, ci, sj, cj;
+        sincos(d.va[i], &si, &ci);
+        sincos(d.va[j], &sj, &cj);
+        const double vir = d.vm[i] * ci, vii = d.vm[i] * si, vjr = d.vm[j] * cj, vji = d.vm[j] * sj;
+        const double2 a = yff[k], b = yft[k], c = ytf[k], e = ytt[k];
+        const double ifr = a.x * vir - a.y * vii + b.x * vjr - b.y * vji;
+        const double ifi = a.x * vii + a.y * vir + b.x * vji + b.y * vjr;
+        const double itr = c.x * vir - c.y * vii + e.x * vjr - e.y * vji;
+        const double iti = c.x * vii + c.y * vir + e.x * vji + e.y * vjr;
+        o[0LL * nbr + k] = vir * ifr + vii * ifi;
+        o[1LL * nbr + k] = vii * ifr - vir * ifi;
+        o[2LL * nbr + k] = vjr * itr + vji * iti;
+        o[3LL * nbr + k] = vji * itr - vjr * iti;
+        o[4LL * nbr + k] = hypot(ifr, ifi);
+        o[5LL * nbr + k] = atan2(ifi, ifr);
+        o[6LL * nbr + k] = hypot(itr, iti);
+        o[7LL * nbr + k] = atan2(iti, itr);
+    }
+}
+
 }  // namespace
+
+void NrContext::set_branches(int64_t nbr_, const int64_t* from, const int64_t* to, const double* yff, const double* yft,
+                             const double* ytf, const double* ytt, const int8_t* status) {
+    if (!n) throw std::logic_error("nr_setup has not been called");
+    if (nbr_ <= 0 || !from || !to || !yff || !yft || !ytf || !ytt || !status)
+        throw std::invalid_argument("nr_set_branches: null or empty input");
+    nbr = (int)nbr_;
+    std::vector<int> f(nbr), t(nbr);
+    for (int k = 0; k < nbr; ++k) {
+        if (from[k] < 1 || from[k] > n || to[k] < 1 || to[k] > n)
+            throw std::invalid_argument("nr_set_branches: bus index out of range");
+        f[k] = (int)from[k] - 1;
+        t[k] = (int)to[k] - 1;
+    }
+    d_brfrom.upload(f, stream);
+    d_brto.upload(t, stream);
+    d_yff.upload(reinterpret_cast<const double2*>(yff), nbr, stream);
+    d_yft.upload(reinterpret_cast<const double2*>(yft), nbr, stream);
+    d_ytf.upload(reinterpret_cast<const double2*>(ytf), nbr, stream);
+    d_ytt.upload(reinterpret_cast<const double2*>(ytt), nbr, stream);
+    d_brstatus.upload(reinterpret_cast<const signed char*>(status), nbr, stream);
+    d_pw.alloc(2 * (size_t)n + 8 * (size_t)nbr);
+    JGB_CUDA(cudaStreamSynchronize(stream));
+}
+
+void NrContext::power(double* out[10]) {
+    if (!have_state) throw std::logic_error("no state on the device");
+    if (!nbr) throw std::logic_error("nr_set_branches must precede nr_power");
+    NrDev d = view(1, false);
+    const int work = n + nbr;
+    nr_power_kernel<<<ceil_div(work, 128), 128, 0, stream>>>(d, nbr, d_brfrom.p, d_brto.p, d_yff.p, d_yft.p, d_ytf.p,
+                                                             d_ytt.p, d_brstatus.p, d_pw.p);
+    ++launches;
+    JGB_CUDA(cudaGetLastError());
+    for (int q = 0; q < 10; ++q) {
+        if (!out[q]) continue;
+        const size_t off = q < 2 ? (size_t)q * n : 2 * (size_t)n + (size_t)(q - 2) * nbr;
+        JGB_CUDA(cudaMemcpyAsync(out[q], d_pw.p + off, (q < 2 ? n : nbr) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    JGB_CUDA(cudaStreamSynchronize(stream));
+}
 
 void NrContext::setup(int64_t n_, const int64_t* ycp, const int64_t* yrv, const double* y, const double* yt,
                       const int8_t* type, int64_t slack_) {

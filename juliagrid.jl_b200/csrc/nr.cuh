@@ -53,6 +53,9 @@ class NrContext {
     int batch(int64_t S, const int64_t* of, const int64_t* ot, const double* dy, bool dev_in, int64_t max_iter,
               double tol, double* vm_out, double* va_out, int32_t* iters, int8_t* status, bool dev_out,
               int64_t* total);
+    void set_branches(int64_t nbr, const int64_t* from, const int64_t* to, const double* yff, const double* yft,
+                      const double* ytf, const double* ytt, const int8_t* status);
+    void power(double* out[10]);
     double stat(const std::string& key);
 
     // host mirrors (the reference's own index arrays, 1-based)
@@ -72,7 +75,11 @@ class NrContext {
     MfSolver solver_batch;   // scenario batches (throughput-oriented amalgamation)
     DevBuf<int> d_ycolptr, d_yrow, d_pq, d_pvpq, d_pcount, d_jcolptr;
     DevBuf<double2> d_y, d_yt;
-    DevBuf<signed char> d_type;
+    DevBuf<signed char> d_type, d_brstatus;
+    DevBuf<int> d_brfrom, d_brto;
+    DevBuf<double2> d_yff, d_yft, d_ytf, d_ytt;
+    DevBuf<double> d_pw;
+    int nbr = 0;
     DevBuf<double> d_sup_p, d_sup_q, d_dem_p, d_dem_q;
     // single-case state (S = 1)
     DevBuf<double> d_vm, d_va, d_f, d_jval, d_inc, d_stop;

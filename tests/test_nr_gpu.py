@@ -160,3 +160,25 @@ def test_bad_arguments(ctx):
     c2 = jgb200.Context(0)
     assert c2.lib.jgb_nr_mismatch(c2.handle, None, None) == -1     # setup not called
     c2.close()
+
+
+@pytest.mark.parametrize("case", ["case14test", "case30test", "synthetic10k"])
+def test_power_postprocessing_on_device(case, ctx):
+    """power!/current! on the device vs the oracle and, for the IEEE cases, vs the MATPOWER goldens
+    asserted by testPower (test/utility/utility.jl:43-59)."""
+    from oracle import post
+    a, o = _pair(case, ctx)
+    assert jgb200.power_flow(a) and onr.power_flow(o)
+    pw = jgb200.power_device(a)
+    ref = post.powers(o.sys, o.mdl, o.vm, o.va)
+    for k in ref:
+        np.testing.assert_allclose(pw[k], ref[k], rtol=1e-9, atol=1e-10, err_msg=k)
+    host = jgb200.power(a.system, a.voltage.magnitude, a.voltage.angle)
+    for k in host:
+        np.testing.assert_allclose(pw[k], host[k], rtol=1e-9, atol=1e-10, err_msg=k)
+    if case != "synthetic10k":
+        g = golden(case)["newtonRaphson"]
+        for ours, theirs in (("injection_active", "injectionActive"), ("injection_reactive", "injectionReactive"),
+                             ("from_active", "fromActive"), ("from_reactive", "fromReactive"),
+                             ("to_active", "toActive"), ("to_reactive", "toReactive")):
+            np.testing.assert_allclose(pw[ours], g[theirs], rtol=1.5e-8, atol=1e-10, err_msg=ours)
