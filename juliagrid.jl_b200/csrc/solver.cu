@@ -418,12 +418,30 @@ mf_factor_bulk_kernel(DevSym sy, const int* __restrict__ fronts, const double* _
     const int c0 = sy.f_childptr[f], c1 = sy.f_childptr[f + 1];
 
     if (threadIdx.x == 0 && c1 > c0) mbar_init(&mbar, 1);
+    // matrix entries: the first NPRE per lane are fetched into registers before the front is zeroed, so their
+    // index -> value load chain overlaps the zeroing pass and the barrier instead of following them
+    constexpr int NPRE = 6;
+    const double* __restrict__ av = aval + s;
+    const int a0 = sy.f_asmptr[f], a1 = sy.f_asmptr[f + 1];
+    int pdst[NPRE];
+    double pval[NPRE];
+#pragma unroll
+    for (int q = 0; q < NPRE; ++q) {
+        const int a = a0 + e0 + q * TE;
+        pdst[q] = -1;
+        pval[q] = 0.0;
+        if (a < a1) {
+            pdst[q] = sy.asm_dst[a];
+            pval[q] = av[(long long)sy.asm_src[a] * S];
+        }
+    }
     for (int pos = e0; pos < fsz; pos += TE) Fl[pos * 32] = 0.0;
     __syncthreads();
     {
-        const double* __restrict__ av = aval + s;
-        const int a1 = sy.f_asmptr[f + 1];
-        for (int a = sy.f_asmptr[f] + e0; a < a1; a += TE) Fl[sy.asm_dst[a] * 32] = av[(long long)sy.asm_src[a] * S];
+#pragma unroll
+        for (int q = 0; q < NPRE; ++q)
+            if (pdst[q] >= 0) Fl[pdst[q] * 32] = pval[q];
+        for (int a = a0 + e0 + NPRE * TE; a < a1; a += TE) Fl[sy.asm_dst[a] * 32] = av[(long long)sy.asm_src[a] * S];
         for (int p = e0; p < k; p += TE) Fl[(p + nf * nf) * 32] = rhs[(long long)rows[p] * S + s];
     }
     uint32_t parity = 0;
