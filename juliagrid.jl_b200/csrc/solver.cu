@@ -394,7 +394,7 @@ constexpr int kBulkMaxChildren = 32;   // children staged per group
 // 256-byte lines. Shared memory: [front nf*(nf+1)*32 doubles][staging cap*32 doubles][rel list cap ints].
 template <int TE, int MAXNF>
 __global__ void __launch_bounds__(32 * TE)
-mf_factor_bulk_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ aval,
+mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const double* __restrict__ aval,
                       const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S,
                       int smem_elems, const unsigned char* __restrict__ active, int* __restrict__ status) {
     extern __shared__ __align__(128) double sm[];
@@ -403,26 +403,26 @@ mf_factor_bulk_kernel(DevSym sy, const int* __restrict__ fronts, const double* _
     constexpr int TR = TE >= 4 ? 4 : TE, TC = TE / TR;
     const int sl = threadIdx.x & 31, e0 = threadIdx.x >> 5;
     const int er = e0 % TR, ec = e0 / TR;
-    const int f = fronts[blockIdx.x];
+    const FrontDesc fd = descs[blockIdx.x];          // one 64-byte read: no dependent metadata loads
     const int s = blockIdx.y * 32 + sl;
     const bool act = active ? (active[s] != 0) : true;
     if (!__syncthreads_or(act)) return;
-    const int nf = sy.f_nf[f], k = sy.f_k[f], u = nf - k;
-    const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
+    const int nf = fd.nf, k = fd.k, u = nf - k;
+    const int* __restrict__ rows = sy.f_rows + fd.rowptr;
     const int fsz = nf * (nf + 1);
     double* Fl = sm + sl;
     double* stage = sm + fsz * 32;
     const int cap = smem_elems - fsz;
     int* srel = reinterpret_cast<int*>(sm + (size_t)smem_elems * 32);
     double* __restrict__ uptile = upd + (long long)blockIdx.y * sy.upd_size * 32;
-    const int c0 = sy.f_childptr[f], c1 = sy.f_childptr[f + 1];
+    const int c0 = fd.child0, c1 = fd.child1;
 
     if (threadIdx.x == 0 && c1 > c0) mbar_init(&mbar, 1);
-    // matrix entries: the first NPRE per lane are fetched into registers before the front is zeroed, so their
-    // index -> value load chain overlaps the zeroing pass and the barrier instead of following them
+    // matrix entries and right-hand side: the first few per lane are fetched into registers before the front is
+    // zeroed, so their index -> value load chains overlap the zeroing pass and the barrier instead of following them
     constexpr int NPRE = 6;
     const double* __restrict__ av = aval + s;
-    const int a0 = sy.f_asmptr[f], a1 = sy.f_asmptr[f + 1];
+    const int a0 = fd.asm0, a1 = fd.asm1;
     int pdst[NPRE];
     double pval[NPRE];
 #pragma unroll
@@ -435,6 +435,13 @@ mf_factor_bulk_kernel(DevSym sy, const int* __restrict__ fronts, const double* _
             pval[q] = av[(long long)sy.asm_src[a] * S];
         }
     }
+    constexpr int NPRE_R = 2;
+    double prhs[NPRE_R];
+#pragma unroll
+    for (int q = 0; q < NPRE_R; ++q) {
+        const int p = e0 + q * TE;
+        prhs[q] = (p < k) ? rhs[(long long)rows[p] * S + s] : 0.0;
+    }
     for (int pos = e0; pos < fsz; pos += TE) Fl[pos * 32] = 0.0;
     __syncthreads();
     {
@@ -442,7 +449,12 @@ mf_factor_bulk_kernel(DevSym sy, const int* __restrict__ fronts, const double* _
         for (int q = 0; q < NPRE; ++q)
             if (pdst[q] >= 0) Fl[pdst[q] * 32] = pval[q];
         for (int a = a0 + e0 + NPRE * TE; a < a1; a += TE) Fl[sy.asm_dst[a] * 32] = av[(long long)sy.asm_src[a] * S];
-        for (int p = e0; p < k; p += TE) Fl[(p + nf * nf) * 32] = rhs[(long long)rows[p] * S + s];
+#pragma unroll
+        for (int q = 0; q < NPRE_R; ++q) {
+            const int p = e0 + q * TE;
+            if (p < k) Fl[(p + nf * nf) * 32] = prhs[q];
+        }
+        for (int p = e0 + NPRE_R * TE; p < k; p += TE) Fl[(p + nf * nf) * 32] = rhs[(long long)rows[p] * S + s];
     }
     uint32_t parity = 0;
     for (int ci = c0; ci < c1;) {
@@ -504,7 +516,7 @@ mf_factor_bulk_kernel(DevSym sy, const int* __restrict__ fronts, const double* _
         for (int i = 0; i < MAXNF; ++i) col[q][i] = (c <= nf && i < nf) ? Fl[(i + c * nf) * 32] : 0.0;
     }
     bool bad = false;
-    double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
+    double* __restrict__ Uf = U + fd.uoff * S + s;
 #pragma unroll
     for (int p = 0; p < MAXNF; ++p) {
         if (p >= k) break;
@@ -538,7 +550,7 @@ mf_factor_bulk_kernel(DevSym sy, const int* __restrict__ fronts, const double* _
     }
     if (!act) return;
     if (bad && e0 == 0) status[s] = -3;
-    double* __restrict__ Cf = uptile + sy.f_updoff[f] * 32 + sl;
+    double* __restrict__ Cf = uptile + fd.updoff * 32 + sl;
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
         const int c = e0 + q * TE;
@@ -570,7 +582,7 @@ void launch_factor(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st,
 // (lanes per scenario, register bound on the front order) variants of the bulk kernel
 #define JGB_BULK_VARIANTS(X) X(4, 8) X(4, 12) X(8, 16) X(8, 20)
 
-void launch_factor_bulk(int maxnf, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const int* fronts,
+void launch_factor_bulk(int maxnf, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const FrontDesc* fronts,
                         const double* aval, const double* rhs, double* U, double* upd, int S, int smem_elems,
                         const unsigned char* active, int* status) {
 #define X(TE, MAXNF)                                                                                              \
@@ -727,6 +739,21 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
     d_ea_roundptr.upload(sym.ea_roundptr, st);
     d_ea_pair.upload(sym.ea_pair, st);
     d_level_fronts.upload(sym.level_fronts, st);
+    {
+        std::vector<FrontDesc> descs(sym.level_fronts.size());
+        for (size_t q = 0; q < descs.size(); ++q) {
+            const int f = sym.level_fronts[q];
+            FrontDesc& d = descs[q];
+            d.f = f; d.nf = sym.f_nf[f]; d.k = sym.f_k[f]; d.rowptr = sym.f_rowptr[f];
+            d.asm0 = sym.f_asmptr[f]; d.asm1 = sym.f_asmptr[f + 1];
+            d.child0 = sym.f_childptr[f]; d.child1 = sym.f_childptr[f + 1];
+            d.ea0 = sym.f_eaptr[f]; d.ea1 = sym.f_eaptr[f + 1];
+            d.pad0 = d.pad1 = 0;
+            d.uoff = sym.f_uoff[f]; d.updoff = sym.f_updoff[f];
+        }
+        d_level_desc.upload(descs, st);
+        JGB_CUDA(cudaStreamSynchronize(st));
+    }
     d_depth_fronts.upload(sym.depth_fronts, st);
     std::vector<long long> uo(sym.f_uoff.begin(), sym.f_uoff.end()), po(sym.f_updoff.begin(), sym.f_updoff.end());
     d_f_uoff.upload(uo, st);
@@ -937,7 +964,7 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
     for (const FactorLaunch& fl : fplan) {
         dim3 grid(fl.count, S / fl.ts);
         if (fl.bulk)
-            launch_factor_bulk(fl.maxnf, grid, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,
+            launch_factor_bulk(fl.maxnf, grid, fl.smem, st, dev, d_level_desc.p + fl.begin, aval, rhs, d_U.p,
                                d_upd.p, S, fl.smem_elems, active, status);
         else if (fl.global_front)
             launch_factor<true>(fl.ts, grid, fl.threads, fl.smem, st, dev, d_level_fronts.p + fl.begin, aval, rhs, d_U.p,

@@ -18,6 +18,14 @@ struct DevSym {
     long long upd_size;
 };
 
+// Per-front descriptor, laid out in launch order (one 64-byte read replaces the fronts[] -> f_* double indirection)
+struct __align__(16) FrontDesc {
+    int f, nf, k, rowptr;
+    int asm0, asm1, child0, child1;
+    int ea0, ea1, pad0, pad1;
+    long long uoff, updoff;
+};
+
 struct FactorLaunch {
     int begin, count;      // range in level_fronts
     int ts;                // scenarios per CTA
@@ -63,6 +71,7 @@ class MfSolver {
         d_asm_src, d_asm_dst, d_level_fronts, d_depth_fronts, d_f_eaptr, d_ea_roundptr, d_ea_pair;
     DevBuf<long long> d_f_uoff, d_f_updoff;
     DevBuf<double> d_U, d_upd, d_gwork;
+    DevBuf<FrontDesc> d_level_desc;
     DevSym dev{};
 };
 
