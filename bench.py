@@ -366,6 +366,22 @@ def run_ours(args):
             single["wls_monte_carlo_gn_iterations_per_s"] = rb.total_iterations / (time.perf_counter() - t0)
             single["wls_monte_carlo_draws"] = Sm
             single["wls_monte_carlo_all_converged"] = bool((rb.status == 0).all())
+            # CPU restatement of the same single-case estimation (C normalEquation! loops + SciPy SpGEMM + SuperLU)
+            jgb200.set_mean(se, z)
+            jgb200.set_voltage_se(se, ps.vm, ps.va)
+            jgb200.state_estimation(se)
+            import oracle
+            from oracle import wls as owls
+            from oracle.fast import FastNR, FastWLS
+            osys = oracle.synthetic_grid()
+            og = owls.gauss_newton(osys, mon, oracle.ac_model(osys), lu_options=FastNR.NOPIVOT)
+            og.mean[:] = z
+            fw = FastWLS(og)
+            t0 = time.perf_counter()
+            fw.state_estimation()
+            single["wls_cpu_baseline_gn_iterations_per_s"] = fw.iteration / (time.perf_counter() - t0)
+            single["wls_cpu_vs_gpu_max_abs_voltage_difference"] = float(
+                max(np.abs(fw.vm - se.voltage.magnitude).max(), np.abs(fw.va - se.voltage.angle).max()))
         except Exception as e:      # the WLS extras must never sink the headline line
             single["wls_error"] = str(e)
 

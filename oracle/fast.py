@@ -106,3 +106,100 @@ class FastNR:
                 return False
             self.solve()
         return False
+
+
+class FastWLS:
+    """Gauss-Newton WLS with the C normalEquation! loops (codes 1, 6-11, 16, 17; diagonal precision), SciPy SpGEMM for
+    H'WH like the reference's two stdlib SpGEMMs, and SuperLU with the symmetric no-pivot settings for the gain."""
+
+    def __init__(self, g, lu_options=None):
+        from . import wls as _w
+        self.g = g
+        sysm, m = g.sys, g.mdl
+        n = sysm.n
+        self.n = n
+        i64 = lambda a: np.ascontiguousarray(a, dtype=np.int64)
+        f64 = lambda a: np.ascontiguousarray(a, dtype=np.float64)
+        self.ycolptr, self.yrowval = i64(m.colptr), i64(m.rowval)
+        self.y = np.ascontiguousarray(m.nzval, dtype=np.complex128).view(np.float64).copy()
+        self.yt = np.ascontiguousarray(m.nzval_t, dtype=np.complex128).view(np.float64).copy()
+        self.ydiag = i64([m.position(i, i) for i in range(n)])
+        self.frm, self.to = i64(sysm.frm), i64(sysm.to)
+        self.bg, self.bb = f64(m.admittance.real), f64(m.admittance.imag)
+        self.bgsi, self.bbsi = f64(0.5 * sysm.g), f64(0.5 * sysm.b)
+        self.btinv, self.bphi = f64(1 / sysm.tap), f64(sysm.shift)
+        self.type, self.index = np.ascontiguousarray(g.type, dtype=np.int8), i64(g.index)
+        # per-row H positions in the semantic slot order of the kernel / C loop
+        H = sp.csc_matrix((np.arange(1, len(g.h_rowval) + 1), g.h_rowval, g.h_colptr), shape=(g.m, 2 * n)).tocsr()
+        slotptr, slotpos = [0], []
+        for r in range(g.m):
+            code, k = int(g.type[r]), int(g.index[r])
+            cols = {}
+            for q in range(H.indptr[r], H.indptr[r + 1]):
+                cols[int(H.indices[q])] = int(H.data[q]) - 1
+            if code == 1:
+                slotpos.append(cols[k + n])
+            elif code in (6, 9):
+                for p in range(m.colptr[k], m.colptr[k + 1]):
+                    j = int(m.rowval[p])
+                    slotpos += [cols[j], cols[j + n]]
+            elif code in (16, 17):
+                slotpos += [cols[k], cols[k + n]]
+            elif code != 0:
+                i, j = int(sysm.frm[k]), int(sysm.to[k])
+                slotpos += [cols[i], cols[i + n], cols[j], cols[j + n]]
+            slotptr.append(len(slotpos))
+        self.slotptr, self.slotpos = i64(slotptr), i64(slotpos)
+        self.wdiag = f64(g.w.diagonal())
+        self.mean = f64(g.mean)
+        self.vm0, self.va0 = g.vm.copy(), g.va.copy()
+        self.vm, self.va = g.vm.copy(), g.va.copy()
+        self.res = np.zeros(g.m)
+        self.hnz = g.h_nzval.copy()
+        self.hrow, self.hcolptr = g.h_rowval.astype(np.int32), g.h_colptr.astype(np.int32)
+        self.lu_options = lu_options or FastNR.NOPIVOT
+        self.W = sp.diags(self.wdiag).tocsc()
+        self.iteration = 0
+        self.objective = 0.0
+
+    def reset(self):
+        self.vm[:] = self.vm0
+        self.va[:] = self.va0
+
+    def increment(self):
+        L = lib()
+        L.owls_normal_equation.restype = C.c_double
+        P = lambda a, t=C.c_int64: _p(a, t)
+        D = lambda a: _p(a, C.c_double)
+        self.objective = L.owls_normal_equation(
+            C.c_int64(self.n), C.c_int64(self.g.m), P(self.ycolptr), P(self.yrowval), D(self.y), D(self.yt),
+            P(self.ydiag), P(self.frm), P(self.to), D(self.bg), D(self.bb), D(self.bgsi), D(self.bbsi), D(self.btinv),
+            D(self.bphi), _p(self.type, C.c_int8), P(self.index), P(self.slotptr), P(self.slotpos), D(self.wdiag),
+            D(self.mean), D(self.vm), D(self.va), D(self.res), D(self.hnz))
+        if self.objective != self.objective:
+            raise ValueError("measurement code outside the C oracle's set")
+        n, sl = self.n, self.g.slack
+        lo, hi = self.hcolptr[sl], self.hcolptr[sl + 1]
+        saved = self.hnz[lo:hi].copy()
+        self.hnz[lo:hi] = 0.0
+        H = sp.csc_matrix((self.hnz, self.hrow, self.hcolptr), shape=(self.g.m, 2 * n))
+        temp = (H.T @ self.W).tocsc()
+        gain = (temp @ H).tolil()
+        gain[sl, sl] = 1.0
+        inc = spla.splu(gain.tocsc(), **self.lu_options).solve(temp @ self.res)
+        inc[sl] = 0.0
+        self.hnz[lo:hi] = saved
+        self.inc = inc
+        return float(np.max(np.abs(inc)))
+
+    def state_estimation(self, iteration=40, tolerance=1e-8):
+        self.iteration = 0
+        for _ in range(iteration + 1):
+            if self.increment() < tolerance:
+                return True
+            if self.iteration == iteration:
+                return False
+            self.va += self.inc[:self.n]
+            self.vm += self.inc[self.n:]
+            self.iteration += 1
+        return False

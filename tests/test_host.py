@@ -171,3 +171,29 @@ def test_shard_bounds_cover_everything():
             assert all(pieces[i][1] == pieces[i + 1][0] for i in range(world - 1))
             sizes = [b - a for a, b in pieces]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_c_wls_oracle_matches_numpy_oracle():
+    """oracle/csrc/oracle_wls.c (CPU baseline for the WLS numbers) == oracle/wls.py on the benchmark measurement set."""
+    from oracle.fast import FastNR, FastWLS
+    os_, ps = oracle_system("synthetic20"), product_system("synthetic20")
+    ps.model = jgb200.ac_model(ps)
+    o = onr.newton_raphson(os_)
+    assert onr.power_flow(o)
+    pw = jgb200.power(ps, o.vm, o.va)
+    mon = jgb200.measurement(ps)
+    jgb200.add_voltmeter(mon, o.vm)
+    jgb200.add_wattmeter(mon, pw)
+    jgb200.add_varmeter(mon, pw)
+    jgb200.add_pmu(mon, pw, o.vm, o.va, buses=range(0, ps.n, 10), polar=False)
+    mon.watt["status"][7] = 0
+    g = owls.gauss_newton(os_, mon, o.mdl, lu_options=FastNR.NOPIVOT)
+    g.mean += 1e-3 * np.random.default_rng(3).standard_normal(g.m)
+    fw = FastWLS(g)
+    assert fw.increment() == pytest.approx(owls.increment(g), rel=1e-12)
+    assert np.array_equal(fw.res, g.residual) and np.array_equal(fw.hnz, g.h_nzval)
+    assert fw.objective == pytest.approx(g.objective, rel=1e-13)
+    fw.reset()
+    assert fw.state_estimation() and owls.state_estimation(g)
+    assert fw.iteration == g.iteration
+    np.testing.assert_allclose(fw.vm, g.vm, atol=1e-12)
