@@ -56,3 +56,48 @@ def test_base_case_scenario_equals_power_flow(ctx):
     for s in range(3):
         np.testing.assert_allclose(res.vm[s], a.voltage.magnitude, atol=1e-13)
         assert res.iterations[s] == a.method.iteration == 4
+
+
+@pytest.mark.parametrize("S", [1, 5, 33])
+def test_ragged_batch_sizes(S, ctx):
+    """Batch sizes that are not multiples of the 32-scenario tile (padding lanes must not leak into the results)."""
+    ps = product_system("case30test")
+    a = jgb200.newton_raphson(ps, ctx)
+    elig = jgb200.eligible_outages(ps)
+    ks = elig[np.arange(S) % len(elig)]
+    res = jgb200.nr_batch(a, ks)
+    assert res.vm.shape == (S, ps.n) and (res.status == 0).all()
+    ref = jgb200.nr_batch(a, ks[:1])
+    np.testing.assert_allclose(res.vm[0], ref.vm[0], atol=1e-13)
+    if S > 1:
+        same = np.flatnonzero(ks == ks[0])
+        for q in same:
+            np.testing.assert_array_equal(res.vm[q], res.vm[0])
+
+
+def test_activsg10k_contingency_batch(ctx):
+    """Secondary 10k configuration (the reference's own case_ACTIVSg10k): outages from the stored profile."""
+    ps = product_system("case_ACTIVSg10k")
+    a = jgb200.newton_raphson(ps, ctx)
+    elig = jgb200.eligible_outages(ps)
+    assert len(elig) == 8729
+    ks = elig[::137][:64]
+    res = jgb200.nr_batch(a, ks)
+    ok = res.status == 0
+    assert ok.mean() > 0.9            # a few outages of this stressed case do not converge within 20 iterations
+    k = int(ks[np.flatnonzero(ok)[3]])
+    jgb200.update_branch(a, k, 0)
+    jgb200.set_initial_point(a)
+    assert jgb200.power_flow(a)
+    pos = int(np.flatnonzero(ks == k)[0])
+    np.testing.assert_allclose(res.vm[pos], a.voltage.magnitude, atol=1e-10)
+    np.testing.assert_allclose(res.va[pos], a.voltage.angle, atol=1e-10)
+    assert res.iterations[pos] == a.method.iteration
+
+
+def test_batch_rejects_bad_arguments(ctx):
+    ps = product_system("case14test")
+    a = jgb200.newton_raphson(ps, ctx)
+    lib = ctx.lib
+    assert lib.jgb_nr_batch(ctx.handle, 0, None, None, None, 20, 1e-8, None, None, None, None, None) == -1
+    assert lib.jgb_nr_run(ctx.handle, -1, 1e-8, None, None, None) == -1
