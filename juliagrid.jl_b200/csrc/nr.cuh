@@ -10,6 +10,7 @@ namespace jgb {
 
 struct NrDev {
     int n, slack, dim, nnzj;
+    int strip_cap;        // entries of the largest staged Ybus strip (batch assembly)
     const int* ycolptr;
     const int* yrow;
     const double2* y;     // Y[row, col]   (nodalMatrix.nzval)
@@ -59,7 +60,7 @@ class NrContext {
     double stat(const std::string& key);
 
     // host mirrors (the reference's own index arrays, 1-based)
-    int n = 0, slack = -1, dim = 0, nnzj = 0, nnzy = 0;
+    int n = 0, slack = -1, dim = 0, nnzj = 0, nnzy = 0, strip_cap = 8;
     std::vector<int64_t> pq1, pvpq1, pcount1, jcolptr1, jrowval1;
     long long launches = 0;
     PhaseTimer timer;
@@ -99,6 +100,7 @@ class NrContext {
     PinnedBuf<int> h_int;
     int64_t iteration = 0;
     bool graphs_disabled = getenv("JGB_NO_GRAPH") != nullptr;
+    bool staged_assembly = getenv("JGB_STAGED_ASSEMBLY") != nullptr;
     bool jac_valid = false;
     bool have_injection = false, have_state = false;
 };
