@@ -399,7 +399,8 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
                       int smem_elems, const unsigned char* __restrict__ active, int* __restrict__ status) {
     extern __shared__ __align__(128) double sm[];
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ int s_off[kBulkMaxChildren], s_uc[kBulkMaxChildren], s_relo[kBulkMaxChildren], s_gend;
+    __shared__ int s_off[kBulkMaxChildren], s_uc[kBulkMaxChildren], s_relo[kBulkMaxChildren], s_relp[kBulkMaxChildren], s_gend;
+    __shared__ long long s_updoff[kBulkMaxChildren];
     constexpr int TR = TE >= 4 ? 4 : TE, TC = TE / TR;
     const int sl = threadIdx.x & 31, e0 = threadIdx.x >> 5;
     const int er = e0 % TR, ec = e0 / TR;
@@ -458,30 +459,34 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
     }
     uint32_t parity = 0;
     for (int ci = c0; ci < c1;) {
+        // child descriptors of up to kBulkMaxChildren children: one parallel 16-byte read each (no dependent chain)
+        const int ncand = min(c1 - ci, kBulkMaxChildren);
+        if ((int)threadIdx.x < ncand) {
+            const ChildDesc cd = sy.child_desc[ci + threadIdx.x];
+            s_uc[threadIdx.x] = cd.uc;
+            s_relp[threadIdx.x] = cd.relptr;
+            s_updoff[threadIdx.x] = cd.updoff;
+        }
+        __syncthreads();
         if (threadIdx.x == 0) {
-            int off = 0, ro = 0, g = 0, c2 = ci;
-            while (c2 < c1 && g < kBulkMaxChildren) {
-                const int c = sy.f_children[c2];
-                const int uc = sy.f_nf[c] - sy.f_k[c];
-                const int blk = uc * (uc + 1);
+            int off = 0, ro = 0, g = 0;
+            while (g < ncand) {
+                const int blk = s_uc[g] * (s_uc[g] + 1);
                 if (g > 0 && off + blk > cap) break;
-                s_off[g] = off; s_uc[g] = uc; s_relo[g] = ro;
-                off += blk; ro += uc; ++g; ++c2;
+                s_off[g] = off; s_relo[g] = ro;
+                off += blk; ro += s_uc[g]; ++g;
             }
-            s_gend = c2;
+            s_gend = ci + g;
             mbar_expect_tx(&mbar, (uint32_t)off * 256u);
-            for (int q = 0; q < g; ++q) {
-                const int c = sy.f_children[ci + q];
-                bulk_g2s(stage + (size_t)s_off[q] * 32, uptile + sy.f_updoff[c] * 32, (uint32_t)(s_uc[q] * (s_uc[q] + 1)) * 256u,
+            for (int q = 0; q < g; ++q)
+                bulk_g2s(stage + (size_t)s_off[q] * 32, uptile + s_updoff[q] * 32, (uint32_t)(s_uc[q] * (s_uc[q] + 1)) * 256u,
                          &mbar);
-            }
         }
         __syncthreads();
         const int gend = s_gend;
         // relative indices of the group's children into shared memory while the bulk copies are in flight
         for (int q = ci + e0; q < gend; q += TE) {
-            const int c = sy.f_children[q];
-            const int* __restrict__ rel = sy.f_rel + sy.f_relptr[c];
+            const int* __restrict__ rel = sy.f_rel + s_relp[q - ci];
             const int uc = s_uc[q - ci];
             for (int i = sl; i < uc; i += 32) srel[s_relo[q - ci] + i] = rel[i];
         }
@@ -752,6 +757,14 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
             d.uoff = sym.f_uoff[f]; d.updoff = sym.f_updoff[f];
         }
         d_level_desc.upload(descs, st);
+        std::vector<ChildDesc> cds(sym.f_children.size());
+        for (size_t q = 0; q < cds.size(); ++q) {
+            const int c = sym.f_children[q];
+            cds[q].uc = sym.f_nf[c] - sym.f_k[c];
+            cds[q].relptr = sym.f_relptr[c];
+            cds[q].updoff = sym.f_updoff[c];
+        }
+        d_child_desc.upload(cds, st);
         JGB_CUDA(cudaStreamSynchronize(st));
     }
     d_depth_fronts.upload(sym.depth_fronts, st);
@@ -779,6 +792,7 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
     JGB_BULK_VARIANTS(X)
 #undef X
     dev.upd_size = sym.upd_size;
+    dev.child_desc = d_child_desc.p;
     JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
 }
 

@@ -10,12 +10,14 @@
 
 namespace jgb {
 
+struct ChildDesc;
 struct DevSym {
     const int *f_k, *f_nf, *f_rowptr, *f_rows, *f_relptr, *f_rel, *f_childptr, *f_children, *f_asmptr, *asm_src,
         *asm_dst, *f_eaptr, *ea_roundptr;
     const int2* ea_pair;
     const long long *f_uoff, *f_updoff;
     long long upd_size;
+    const struct ChildDesc* child_desc;
 };
 
 // Per-front descriptor, laid out in launch order (one 64-byte read replaces the fronts[] -> f_* double indirection)
@@ -24,6 +26,12 @@ struct __align__(16) FrontDesc {
     int asm0, asm1, child0, child1;
     int ea0, ea1, pad0, pad1;
     long long uoff, updoff;
+};
+
+// Per-child descriptor in f_children order: what a parent needs to fetch and scatter a child's update block
+struct __align__(16) ChildDesc {
+    int uc, relptr;
+    long long updoff;
 };
 
 struct FactorLaunch {
@@ -72,6 +80,7 @@ class MfSolver {
     DevBuf<long long> d_f_uoff, d_f_updoff;
     DevBuf<double> d_U, d_upd, d_gwork;
     DevBuf<FrontDesc> d_level_desc;
+    DevBuf<ChildDesc> d_child_desc;
     DevSym dev{};
 };
 
