@@ -1,5 +1,5 @@
 #!/bin/bash
-run() { echo "== relax $1"; JGB_RELAX="$1" python scripts/quick_time2.py 1024 single 2>&1 | grep -E "batch S|single NR"; JGB_RELAX="$1" python -c "
+run() { echo "== relax $1"; JGB_RELAX="$1" python scripts/time_nr.py 1024 single 2>&1 | grep -E "batch S|single NR"; JGB_RELAX="$1" python -c "
 import jgb200
 ps=jgb200.synthetic_grid(); ctx=jgb200.Context(0); a=jgb200.newton_raphson(ps,ctx)
 print({k:ctx.stat('nr.'+k) for k in ('fronts','levels','nnz_lu','flops','max_front','u_size','upd_size')})"; }
