@@ -25,7 +25,7 @@ struct SymbolicOptions {
 inline SymbolicOptions latency_options() { return SymbolicOptions(); }
 inline SymbolicOptions throughput_options() {
     SymbolicOptions o;
-    o.relax_small = 2; o.relax_mid = 8; o.relax_mid_frac = 0.3; o.relax_big = 24; o.relax_big_frac = 0.1;
+    o.relax_small = 4; o.relax_mid = 8; o.relax_mid_frac = 0.3; o.relax_big = 24; o.relax_big_frac = 0.1;
     o.relax_any_frac = 0.02;
     return o;
 }

@@ -1,10 +1,10 @@
 #!/bin/bash
-run() { echo "== relax $1"; JGB_RELAX="$1" python scripts/time_nr.py 1024 single 2>&1 | grep -E "batch S|single NR"; JGB_RELAX="$1" python -c "
-import jgb200
-ps=jgb200.synthetic_grid(); ctx=jgb200.Context(0); a=jgb200.newton_raphson(ps,ctx)
-print({k:ctx.stat('nr.'+k) for k in ('fronts','levels','nnz_lu','flops','max_front','u_size','upd_size')})"; }
-run "4,16,0.5,48,0.15,0.05"
-run "0,0,0,0,0,0"
+# tuning sweep of the supernode amalgamation for batches (JGB_RELAX overrides both presets)
+run() { echo "== relax $1"; JGB_RELAX="$1" python scripts/time_nr.py 2048 2>&1 | grep -E "batch S"; }
 run "2,8,0.3,24,0.1,0.02"
-run "4,8,0.3,16,0.1,0.0"
-run "8,32,0.6,64,0.3,0.1"
+run "3,8,0.3,24,0.1,0.02"
+run "4,8,0.3,24,0.1,0.02"
+run "2,6,0.2,16,0.08,0.02"
+run "2,12,0.4,32,0.12,0.03"
+run "1,4,0.2,16,0.05,0.0"
+run "4,12,0.4,32,0.15,0.03"
