@@ -535,22 +535,21 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
         const double piv = b[p * 32];
         if (piv == 0.0 || !isfinite(piv)) bad = true;
         const double inv = 1.0 / piv;
-        double l[MAXNF];
-#pragma unroll
-        for (int i = p + 1; i < MAXNF; ++i) l[i] = (i < nf) ? b[i * 32] : 0.0;
         double* Urow = Uf + urow_off(p, nf) * S;
+        double m[NC];                                   // multiplier of each owned column, 0 for columns not updated
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
             const int c = e0 + q * TE;
-            if (c >= p && c <= nf) {
-                const double upc = col[q][p];                      // U[p, c]
-                if (act) Urow[(long long)(c - p) * S] = (c == p) ? inv : upc;
-                if (c > p) {
-                    const double m = inv * upc;
+            const double upc = col[q][p];               // U[p, c]
+            const bool in = c >= p && c <= nf;
+            if (act && in) Urow[(long long)(c - p) * S] = (c == p) ? inv : upc;
+            m[q] = (in && c > p) ? inv * upc : 0.0;
+        }
 #pragma unroll
-                    for (int i = p + 1; i < MAXNF; ++i) col[q][i] -= l[i] * m;
-                }
-            }
+        for (int i = p + 1; i < MAXNF; ++i) {
+            const double li = (i < nf) ? b[i * 32] : 0.0;   // pivot-column entry, read once for all owned columns
+#pragma unroll
+            for (int q = 0; q < NC; ++q) col[q][i] -= li * m[q];
         }
     }
     if (!act) return;
@@ -585,7 +584,7 @@ void launch_factor(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st,
 }
 
 // (lanes per scenario, register bound on the front order) variants of the bulk kernel
-#define JGB_BULK_VARIANTS(X) X(4, 8) X(4, 12) X(8, 16) X(8, 20)
+#define JGB_BULK_VARIANTS(X) X(4, 8) X(4, 12) X(8, 16)
 
 void launch_factor_bulk(int maxnf, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const FrontDesc* fronts,
                         const double* aval, const double* rhs, double* U, double* upd, int S, int smem_elems,
@@ -601,7 +600,13 @@ void launch_factor_bulk(int maxnf, dim3 grid, size_t smem, cudaStream_t st, DevS
     throw std::runtime_error("unsupported bulk factor variant");
 }
 
-int bulk_variant_for(int nf) { return nf <= 8 ? 8 : nf <= 12 ? 12 : nf <= 16 ? 16 : nf <= 20 ? 20 : 0; }
+int bulk_variant_for(int nf) {
+    // fronts above 16 go to the shared-memory kernel: a 20-row register variant spilled its columns to local memory
+    // and was 7 % slower on the factor phase than the blocked kernel with 16-scenario tiles
+    static const int bulk_max = getenv("JGB_BULK_MAX") ? atoi(getenv("JGB_BULK_MAX")) : 16;
+    if (nf > bulk_max || nf > 16) return 0;
+    return nf <= 8 ? 8 : nf <= 12 ? 12 : 16;
+}
 int bulk_lanes_for(int maxnf) { return maxnf <= 12 ? 4 : 8; }
 
 template <int TS>
@@ -826,7 +831,7 @@ void MfSolver::plan(int S) {
     // single case: one launch per level (launch latency dominates; measured 625 us vs 855 us per factorisation with
     // four size classes on the 10k-bus Jacobian)
     static const std::vector<PlanRule> single_rules = {{kMaxSmemFront, 1, 256}, {kMaxSymFront, 1, 256}};
-    static const std::vector<PlanRule> batch_rules = {{8, 32, 128}, {12, 32, 128}, {16, 32, 256}, {20, 32, 256},
+    static const std::vector<PlanRule> batch_rules = {{8, 32, 128}, {12, 32, 128}, {16, 32, 256}, {20, 16, 256},
                                                       {24, 8, 256}, {32, 8, 256}, {48, 4, 256}, {64, 2, 256},
                                                       {96, 1, 256}, {kMaxSmemFront, 1, 256},
                                                       {kMaxSymFront, 1, 256}};
