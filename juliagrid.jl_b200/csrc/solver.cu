@@ -150,34 +150,51 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __rest
             }
         }
         __syncthreads();
-        for (int i = pe + er; i < nf; i += TR) {
+        // two rows per lane (i and i + TR) share every pivot-row read: 8 broadcast LDS feed 16 multiply-adds
+        for (int i = pe + er; i < nf; i += 2 * TR) {
+            const int i2 = i + TR;
+            const bool two = i2 < nf;
             double* rowi = Fl + i * TS;
-            double l[B];
+            double* rowi2 = Fl + (two ? i2 : i) * TS;
+            double l[B], l2[B];
 #pragma unroll
-            for (int q = 0; q < B; ++q) l[q] = (q < pb) ? pan[(i + q * nf) * TS] : 0.0;
+            for (int q = 0; q < B; ++q) {
+                l[q] = (q < pb) ? pan[(i + q * nf) * TS] : 0.0;
+                l2[q] = (q < pb && two) ? pan[(i2 + q * nf) * TS] : 0.0;
+            }
             // l[q] is zero beyond the block, so the full-width loop is exact whenever its reads stay inside the front
             // (always for full blocks); the ragged last block takes the predicated form
             if (pb == B) {
-#pragma unroll 2
                 for (int j = pe + ec; j <= nf; j += TC) {
                     const double* uj;
                     if constexpr (GLOBAL_F) uj = Ul + j * B * TS;
                     else uj = Fl + (p0 + j * nf) * TS;
-                    double acc = rowi[j * colstride];
+                    double acc = rowi[j * colstride], acc2 = rowi2[j * colstride];
 #pragma unroll
-                    for (int q = 0; q < B; ++q) acc -= l[q] * uj[q * TS];
+                    for (int q = 0; q < B; ++q) {
+                        const double uq = uj[q * TS];
+                        acc -= l[q] * uq;
+                        acc2 -= l2[q] * uq;
+                    }
                     rowi[j * colstride] = acc;
+                    if (two) rowi2[j * colstride] = acc2;
                 }
             } else {
                 for (int j = pe + ec; j <= nf; j += TC) {
                     const double* uj;
                     if constexpr (GLOBAL_F) uj = Ul + j * B * TS;
                     else uj = Fl + (p0 + j * nf) * TS;
-                    double acc = rowi[j * colstride];
+                    double acc = rowi[j * colstride], acc2 = rowi2[j * colstride];
 #pragma unroll
-                    for (int q = 0; q < B; ++q)
-                        if (q < pb) acc -= l[q] * uj[q * TS];
+                    for (int q = 0; q < B; ++q) {
+                        if (q < pb) {
+                            const double uq = uj[q * TS];
+                            acc -= l[q] * uq;
+                            acc2 -= l2[q] * uq;
+                        }
+                    }
                     rowi[j * colstride] = acc;
+                    if (two) rowi2[j * colstride] = acc2;
                 }
             }
         }
@@ -892,7 +909,7 @@ void MfSolver::plan(int S) {
             }
             int te = fl.threads / fl.ts;
             int trw = 1;
-            while (trw < nf && trw < te) trw *= 2;     // rows first: one lane per front row when the lanes allow
+            while (trw < (nf + 1) / 2 && trw < te) trw *= 2;   // rows first: one lane per pair of front rows
             fl.tr = std::min(pow2_floor(te), trw);
             if (fl.bulk) fl.sym = false;
             if (fl.sym) {
