@@ -136,6 +136,33 @@ int32_t jgb_wls_batch_dev(jgb_ctx* ctx, int64_t S, const double* Z_dev, int64_t 
                           double* vm_out_dev, double* va_out_dev, int32_t* iterations_dev, int8_t* status_dev,
                           double* objective_dev, int64_t* total_iterations);
 
+/* ---- constant-matrix linear solves -------------------------------------------------------------
+ * The reference's linear analyses factor one sparse symmetric matrix and call `solution!` per right-hand side:
+ *   DC power flow      solve!  src/powerFlow/dcPowerFlow.jl:93-134        (B theta = P, slack row/column -> identity)
+ *   DC state estimation solve! src/stateEstimation/dcStateEstimation.jl:342-371   (H'WH theta = H'W z)
+ *   PMU state estimation solve! src/stateEstimation/pmuStateEstimation.jl:369-399 (H'WH [Re V; Im V] = H'W z)
+ * through `factorization / factorization! / solution!` (src/backend/utility.jl:470-586). Here the matrix is factored
+ * once on the device (LDL^T on the fixed elimination tree, no pivoting) and a whole block of right-hand sides — one
+ * per Monte-Carlo draw or injection scenario — is solved with the stored factor. */
+/* == factorization(A, F, T): A is n x n symmetric, full CSC as SparseMatrixCSC{Float64,Int64} (1-based, sorted rows,
+ * both triangles). skip (1-based, 0 = none): row and column `skip` are replaced by the identity (slack bus), so
+ * x[skip] = b[skip]. Returns -3 on a zero / non-finite pivot. */
+int32_t jgb_lin_setup(jgb_ctx* ctx, int64_t n, const int64_t* a_colptr, const int64_t* a_rowval, const double* a_nzval,
+                      int64_t skip);
+/* == factorization!(A, F, T): new values on the pattern given to jgb_lin_setup. */
+int32_t jgb_lin_refactor(jgb_ctx* ctx, const double* a_nzval);
+/* P = precision * coefficient (W H, m x n CSC, 1-based): right-hand sides are formed on the device as b = P' z
+ * (`temp * se.mean`, dcStateEstimation.jl:363, pmuStateEstimation.jl:383). Column `skip` of P is ignored. */
+int32_t jgb_lin_projection(jgb_ctx* ctx, int64_t m, const int64_t* p_colptr, const int64_t* p_rowval,
+                           const double* p_nzval);
+/* == solution!(x, F, b) for R right-hand sides: b and x are [R][n], each vector contiguous. */
+int32_t jgb_lin_solve(jgb_ctx* ctx, int64_t R, const double* b, double* x);
+/* x_r = A^-1 (P' z_r) for R measurement vectors z [R][m]. */
+int32_t jgb_lin_solve_projected(jgb_ctx* ctx, int64_t R, const double* z, double* x);
+/* Same two calls with DEVICE pointers (projected != 0 selects the second form). */
+int32_t jgb_lin_solve_dev(jgb_ctx* ctx, int64_t R, const double* in_dev, double* x_dev, int32_t projected);
+int32_t jgb_lin_dims(jgb_ctx* ctx, int64_t* n, int64_t* m, int64_t* nnz_factor, int64_t* fronts);
+
 /* ---- statistics for roofline reports ------------------------------------------------------------------------ */
 /* key: "nr.nnz_lu", "nr.fronts", "nr.levels", "nr.flops", "nr.max_front", "nr.launches_per_iteration",
  *      "nr.assemble_bytes" (per scenario-iteration), "nr.solve_bytes", "wls.*" likewise; kernel launch counter

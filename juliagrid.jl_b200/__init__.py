@@ -12,4 +12,10 @@ from .measurement import (Measurement, measurement, power, add_voltmeter, add_am
 from .ac_state_estimation import (AcStateEstimation, gauss_newton, increment, solve_se, state_estimation,  # noqa: F401
                                   set_mean, set_voltage_se, gaussNewton, stateEstimation)
 from .batch import BatchResult, eligible_outages, outage_arrays, nr_batch, wls_batch  # noqa: F401
+from .linear_solver import LinearSolver  # noqa: F401
+from .dc_power_flow import DcModel, DcPowerFlow, dc_model, dc_power_flow, solve_dc, dc_batch, power_dc  # noqa: F401
+from .dc_state_estimation import (DcStateEstimation, LinearWls, dc_wls_tables, dc_state_estimation,  # noqa: F401
+                                  solve_dc_se, dc_se_batch)
+from .pmu_state_estimation import (PmuStateEstimation, pmu_wls_tables, pmu_state_estimation, solve_pmu_se,  # noqa: F401
+                                   pmu_se_batch)
 from . import dist  # noqa: F401

@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libjgb200.so")
+LIB_PATH = os.environ.get("JGB200_LIB") or os.path.join(_HERE, "libjgb200.so")
 
 c_i64p = C.POINTER(C.c_int64)
 c_i32p = C.POINTER(C.c_int32)
@@ -81,7 +81,7 @@ def load() -> C.CDLL:
         raise ImportError(f"{LIB_PATH} is missing — build it with `python -c 'import __graft_entry__ as g; "
                           f"g.build()'` (make -C juliagrid.jl_b200/csrc). jgb200 has no CPU fallback.")
     lib = C.CDLL(LIB_PATH)
-    for table in (PROTOTYPES, WLS_PROTOTYPES):
+    for table in (PROTOTYPES, WLS_PROTOTYPES, LIN_PROTOTYPES):
         for name, (res, args) in table.items():
             fn = getattr(lib, name)   # AttributeError here = header / library mismatch
             fn.restype = res
@@ -91,7 +91,18 @@ def load() -> C.CDLL:
 
 
 def exported_symbols():
-    return list(PROTOTYPES) + list(WLS_PROTOTYPES)
+    return list(PROTOTYPES) + list(WLS_PROTOTYPES) + list(LIN_PROTOTYPES)
+
+
+LIN_PROTOTYPES = {
+    "jgb_lin_setup": (C.c_int32, [C.c_void_p, C.c_int64, c_i64p, c_i64p, c_f64p, C.c_int64]),
+    "jgb_lin_refactor": (C.c_int32, [C.c_void_p, c_f64p]),
+    "jgb_lin_projection": (C.c_int32, [C.c_void_p, C.c_int64, c_i64p, c_i64p, c_f64p]),
+    "jgb_lin_solve": (C.c_int32, [C.c_void_p, C.c_int64, c_f64p, c_f64p]),
+    "jgb_lin_solve_projected": (C.c_int32, [C.c_void_p, C.c_int64, c_f64p, c_f64p]),
+    "jgb_lin_solve_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
+    "jgb_lin_dims": (C.c_int32, [C.c_void_p, c_i64p, c_i64p, c_i64p, c_i64p]),
+}
 
 
 def ptr(a: np.ndarray, ctype):

@@ -6,6 +6,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "lin.cuh"
 #include "nr.cuh"
 #include "symbolic.hpp"
 #ifdef JGB_WITH_WLS
@@ -18,6 +19,7 @@ struct jgb_ctx {
     bool own_stream = false;
     std::string err;
     std::unique_ptr<jgb::NrContext> nr;
+    std::unique_ptr<jgb::LinContext> lin;
 #ifdef JGB_WITH_WLS
     std::unique_ptr<jgb::WlsContext> wls;
 #endif
@@ -335,6 +337,53 @@ int32_t jgb_profile(jgb_ctx* ctx, int32_t enable) {
 #ifdef JGB_WITH_WLS
         if (ctx->wls) { ctx->wls->timer.enabled = enable != 0; ctx->wls->timer.reset(); }
 #endif
+        return 0;
+    });
+}
+
+int32_t jgb_lin_setup(jgb_ctx* ctx, int64_t n, const int64_t* a_colptr, const int64_t* a_rowval, const double* a_nzval,
+                      int64_t skip) {
+    return guarded(ctx, [&] {
+        auto lin = std::make_unique<jgb::LinContext>(ctx->stream);
+        lin->setup(n, a_colptr, a_rowval, a_nzval, skip);
+        ctx->lin = std::move(lin);
+        return 0;
+    });
+}
+
+static jgb::LinContext& lin_of(jgb_ctx* ctx) {
+    if (!ctx->lin) throw std::logic_error("jgb_lin_setup has not been called on this context");
+    return *ctx->lin;
+}
+
+int32_t jgb_lin_refactor(jgb_ctx* ctx, const double* a_nzval) {
+    return guarded(ctx, [&] { lin_of(ctx).refactor(a_nzval); return 0; });
+}
+
+int32_t jgb_lin_projection(jgb_ctx* ctx, int64_t m, const int64_t* p_colptr, const int64_t* p_rowval,
+                           const double* p_nzval) {
+    return guarded(ctx, [&] { lin_of(ctx).set_projection(m, p_colptr, p_rowval, p_nzval); return 0; });
+}
+
+int32_t jgb_lin_solve(jgb_ctx* ctx, int64_t R, const double* b, double* x) {
+    return guarded(ctx, [&] { lin_of(ctx).solve(R, b, false, x, false, false); return 0; });
+}
+
+int32_t jgb_lin_solve_projected(jgb_ctx* ctx, int64_t R, const double* z, double* x) {
+    return guarded(ctx, [&] { lin_of(ctx).solve(R, z, false, x, false, true); return 0; });
+}
+
+int32_t jgb_lin_solve_dev(jgb_ctx* ctx, int64_t R, const double* in_dev, double* x_dev, int32_t projected) {
+    return guarded(ctx, [&] { lin_of(ctx).solve(R, in_dev, true, x_dev, true, projected != 0); return 0; });
+}
+
+int32_t jgb_lin_dims(jgb_ctx* ctx, int64_t* n, int64_t* m, int64_t* nnz_factor, int64_t* fronts) {
+    return guarded(ctx, [&] {
+        jgb::LinContext& l = lin_of(ctx);
+        if (n) *n = l.n;
+        if (m) *m = l.m;
+        if (nnz_factor) *nnz_factor = l.nnz_factor();
+        if (fronts) *fronts = l.nfronts();
         return 0;
     });
 }

@@ -738,6 +738,80 @@ void launch_backsolve_tile(int ts, dim3 grid, size_t smem, cudaStream_t st, DevS
 #undef JGB_CASE
 }
 
+// ---- one factorisation, many right-hand sides (symmetric matrices) -------------------------------------------
+// The linear estimators and the DC power flow factor a constant matrix once and solve for a block of right-hand
+// sides (`solution!` per Monte-Carlo draw in the reference). The block B is right-hand-side minor: entry i of
+// column r at B[i * R + r], so a warp's 32 lanes are 32 right-hand sides and every access is a 256-byte line.
+// For a symmetric matrix L = (D^-1 U)^T, so the packed U rows written by the factor kernels (S == 1 layout) are all
+// that is needed: row p holds 1/d_p, then U[p, j] = d_p L[j, p] for the later front rows.
+//
+// Forward substitution, one launch per level (leaves first). CTA = one front x 32 right-hand sides, TE = blockDim / 32
+// lanes per right-hand side split the front rows. A front first gathers its children's contributions (each child
+// wrote its update-row part into its own slot of C, so the sums are ordered and deterministic), eliminates its
+// pivots (one barrier per pivot), overwrites B[pivot rows] with y and leaves its own contribution in C.
+__global__ void __launch_bounds__(256)
+mf_fwd_multi_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ U, double* __restrict__ B,
+                    double* __restrict__ C, const long long* __restrict__ coff, int R) {
+    extern __shared__ double sh[];
+    const int sl = threadIdx.x & 31, e = threadIdx.x >> 5, TE = blockDim.x >> 5;
+    const int r = blockIdx.y * 32 + sl;
+    const int f = fronts[blockIdx.x];
+    const int nf = sy.f_nf[f], k = sy.f_k[f], u = nf - k;
+    const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
+    double* t = sh + sl;                                    // t[i * 32]
+    for (int i = e; i < nf; i += TE) t[i * 32] = (i < k) ? B[(long long)rows[i] * R + r] : 0.0;
+    __syncthreads();
+    for (int ci = sy.f_childptr[f]; ci < sy.f_childptr[f + 1]; ++ci) {
+        const int c = sy.f_children[ci];
+        const int uc = sy.f_nf[c] - sy.f_k[c];
+        const int* __restrict__ rel = sy.f_rel + sy.f_relptr[c];
+        const double* __restrict__ Cc = C + coff[c] * R + r;
+        for (int j = e; j < uc; j += TE) t[rel[j] * 32] += Cc[(long long)j * R];
+        __syncthreads();
+    }
+    const double* __restrict__ Uf = U + sy.f_uoff[f];
+    for (int p = 0; p < k; ++p) {
+        const double* __restrict__ Urow = Uf + urow_off(p, nf);
+        const double y = t[p * 32] * Urow[0];              // y_p / d_p: multiplier of the packed row
+        for (int j = p + 1 + e; j < nf; j += TE) t[j * 32] -= Urow[j - p] * y;
+        __syncthreads();
+    }
+    for (int i = e; i < k; i += TE) B[(long long)rows[i] * R + r] = t[i * 32];
+    double* __restrict__ Cf = C + coff[f] * R + r;
+    for (int j = e; j < u; j += TE) Cf[(long long)j * R] = t[(k + j) * 32];
+}
+
+// Backward substitution, one launch per depth level (roots first): x_p = (y_p - sum_{j>p} U[p,j] x_j) / d_p.
+__global__ void __launch_bounds__(256)
+mf_bwd_multi_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ U, double* __restrict__ B,
+                    int R) {
+    extern __shared__ double sh[];
+    const int sl = threadIdx.x & 31, e = threadIdx.x >> 5, TE = blockDim.x >> 5;
+    const int r = blockIdx.y * 32 + sl;
+    const int f = fronts[blockIdx.x];
+    const int nf = sy.f_nf[f], k = sy.f_k[f];
+    const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
+    double* t = sh + sl;
+    for (int i = e; i < nf; i += TE) t[i * 32] = B[(long long)rows[i] * R + r];
+    __syncthreads();
+    const double* __restrict__ Uf = U + sy.f_uoff[f];
+    for (int p = e; p < k; p += TE) {                       // part of every pivot row that multiplies known x
+        const double* __restrict__ Urow = Uf + urow_off(p, nf);
+        double acc = t[p * 32];
+        for (int j = k; j < nf; ++j) acc -= Urow[j - p] * t[j * 32];
+        t[p * 32] = acc;
+    }
+    __syncthreads();
+    for (int p = k - 1; p >= 0; --p) {
+        if (e == p % TE) t[p * 32] *= Uf[urow_off(p, nf)];
+        __syncthreads();
+        const double xp = t[p * 32];
+        for (int q = e; q < p; q += TE) t[q * 32] -= Uf[urow_off(q, nf) + (p - q)] * xp;
+    }
+    __syncthreads();
+    for (int p = e; p < k; p += TE) B[(long long)rows[p] * R + r] = t[p * 32];
+}
+
 constexpr int kMaxSmemFront = 150;    // nf*(nf+1)*8 bytes must fit the 200 KB dynamic shared-memory budget
 
 int pow2_floor(int v) {
@@ -751,6 +825,8 @@ int pow2_floor(int v) {
 void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) {
     sym = s;
     symmetric = symmetric_matrix;
+    d_coff.release();
+    csum = 0;
     d_f_k.upload(sym.f_k, st);
     d_f_nf.upload(sym.f_nf, st);
     d_f_rowptr.upload(sym.f_rowptr, st);
@@ -1020,6 +1096,43 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
             launch_backsolve_tile(sl.ts, dim3(sl.count, S / sl.ts), sl.smem, st, dev, d_depth_fronts.p + sl.begin,
                                   d_U.p, x, S, active);
         }
+    }
+    JGB_CUDA(cudaGetLastError());
+}
+
+void MfSolver::solve_multi(double* B, int R, cudaStream_t st) {
+    if (!symmetric) throw std::logic_error("solve_multi needs a symmetric matrix");
+    if (planned_S != 1) throw std::logic_error("solve_multi: factor the matrix (S = 1) first");
+    if (R <= 0 || R % 32 != 0) throw std::invalid_argument("solve_multi: the block width must be a multiple of 32");
+    if (d_coff.n == 0) {
+        std::vector<long long> coff(sym.nfronts + 1, 0);
+        for (int f = 0; f < sym.nfronts; ++f) coff[f + 1] = coff[f] + (sym.f_nf[f] - sym.f_k[f]);
+        csum = coff[sym.nfronts];
+        d_coff.upload(coff, st);
+        JGB_CUDA(cudaStreamSynchronize(st));
+        JGB_CUDA(cudaFuncSetAttribute(mf_fwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        JGB_CUDA(cudaFuncSetAttribute(mf_bwd_multi_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    }
+    d_cvec.alloc((size_t)std::max<long long>(csum, 1) * R);
+    auto launch_dims = [&](const int* list, int b, int e, int& threads, size_t& smem) {
+        int mx = 0;
+        for (int q = b; q < e; ++q) mx = std::max(mx, sym.f_nf[list[q]]);
+        threads = mx <= 16 ? 64 : mx <= 64 ? 128 : 256;
+        smem = (size_t)mx * 32 * sizeof(double);
+        if (smem > 200 * 1024) throw std::runtime_error("front too large for the multi right-hand-side solve");
+    };
+    for (int l = 0; l < sym.nlevels; ++l) {
+        const int b = sym.levelptr[l], e = sym.levelptr[l + 1];
+        int threads; size_t smem;
+        launch_dims(sym.level_fronts.data(), b, e, threads, smem);
+        mf_fwd_multi_kernel<<<dim3(e - b, R / 32), threads, smem, st>>>(dev, d_level_fronts.p + b, d_U.p, B, d_cvec.p,
+                                                                          d_coff.p, R);
+    }
+    for (int d = 0; d < sym.ndepths; ++d) {
+        const int b = sym.depthptr[d], e = sym.depthptr[d + 1];
+        int threads; size_t smem;
+        launch_dims(sym.depth_fronts.data(), b, e, threads, smem);
+        mf_bwd_multi_kernel<<<dim3(e - b, R / 32), threads, smem, st>>>(dev, d_depth_fronts.p + b, d_U.p, B, R);
     }
     JGB_CUDA(cudaGetLastError());
 }

@@ -65,6 +65,10 @@ class MfSolver {
     // `active` (nullable, [S]) skips scenarios whose flag is 0. `status[s]` is set to -3 on a zero / non-finite pivot.
     void factor_solve(const double* aval, const double* rhs, double* x, int S, const unsigned char* active,
                       int* status, cudaStream_t st, cudaEvent_t after_factor = nullptr);
+    // After a factor_solve with S == 1 of a symmetric matrix: solve A X = B for a block of R right-hand sides with the
+    // stored factor (`solution!` per draw in the reference, utility.jl:576-586). B is [n][R] (entry i of column r at
+    // B[i * R + r], R a multiple of 32) and is overwritten by X.
+    void solve_multi(double* B, int R, cudaStream_t st);
     int64_t factor_bytes(int S) const;     // algorithmic HBM bytes of one factor_solve (for roofline reports)
     int launches_per_solve(int S);
     int factor_launches(int S) { plan(S); return (int)fplan.size(); }
@@ -78,7 +82,9 @@ class MfSolver {
     DevBuf<int> d_f_k, d_f_nf, d_f_rowptr, d_f_rows, d_f_relptr, d_f_rel, d_f_childptr, d_f_children, d_f_asmptr,
         d_asm_src, d_asm_dst, d_level_fronts, d_depth_fronts, d_f_eaptr, d_ea_roundptr, d_ea_pair;
     DevBuf<long long> d_f_uoff, d_f_updoff;
-    DevBuf<double> d_U, d_upd, d_gwork;
+    DevBuf<double> d_U, d_upd, d_gwork, d_cvec;
+    DevBuf<long long> d_coff;
+    long long csum = 0;
     DevBuf<FrontDesc> d_level_desc;
     DevBuf<ChildDesc> d_child_desc;
     DevSym dev{};

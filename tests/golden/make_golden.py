@@ -47,6 +47,9 @@ def main(ref="/root/reference"):
         for k in res.keys(grp):
             v = res[grp + "/" + k]
             out["newtonRaphson"][k] = np.asarray(v).reshape(-1).tolist()
+        out["dcPowerFlow"] = {k: np.asarray(res[f"/{case}/dcPowerFlow/{k}"]).reshape(-1).tolist()
+                              for k in res.keys(f"/{case}/dcPowerFlow")}
+        out["source"] += f" + /{case}/dcPowerFlow"
         with open(os.path.join(HERE, f"{case}.json"), "w") as fh:
             json.dump(out, fh)
         print(case, "iteration", out["newtonRaphson"]["iteration"])
