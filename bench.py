@@ -384,6 +384,42 @@ def run_ours(args):
                 max(np.abs(fw.vm - se.voltage.magnitude).max(), np.abs(fw.va - se.voltage.angle).max()))
         except Exception as e:      # the WLS extras must never sink the headline line
             single["wls_error"] = str(e)
+        try:
+            # PMU-only linear state estimation, 1024 Monte-Carlo draws on one gain factorisation
+            # (jgb_lin_*), beside SciPy SuperLU (one factorisation, one solve per draw) on one host core
+            import scipy.sparse.linalg as spla
+            pw = jgb200.power(ps, a.voltage.magnitude, a.voltage.angle)
+            mon = jgb200.measurement(ps)
+            jgb200.add_pmu(mon, pw, a.voltage.magnitude, a.voltage.angle, buses=range(n), branch=True, polar=False)
+            keep = mon.pmu["bus"] | (mon.pmu["mag_mean"] > 0.05)
+            mon.pmu = {k: v[keep] for k, v in mon.pmu.items()}
+            pse = jgb200.pmu_state_estimation(mon, ctx)
+            pm = pse.method
+            R = 1024
+            Z = pm.mean[None, :] + 1e-4 * np.random.default_rng(1).standard_normal((R, len(pm.mean)))
+            dZ = torch.from_numpy(Z).cuda()
+            dX = torch.empty((R, 2 * n), dtype=torch.float64, device="cuda")
+            for _ in range(2):
+                pm.solver.solve_dev(R, dZ.data_ptr(), dX.data_ptr(), True)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(5):
+                pm.solver.solve_dev(R, dZ.data_ptr(), dX.data_ptr(), True)
+            torch.cuda.synchronize()
+            single["pmu_se_monte_carlo_draws_per_s"] = 5 * R / (time.perf_counter() - t0)
+            t0 = time.perf_counter()
+            X = pm.solver.solve_projected(Z)
+            single["pmu_se_monte_carlo_draws_per_s_e2e"] = R / (time.perf_counter() - t0)
+            single["pmu_se_rows"] = int(len(pm.mean))
+            h = pm.coefficient.tocsc()
+            wh = (pm.precision @ h).tocsc()
+            lu = spla.splu((h.T @ wh).tocsc())
+            t0 = time.perf_counter()
+            xs = np.stack([lu.solve(wh.T @ Z[r]) for r in range(32)])
+            single["pmu_se_cpu_baseline_draws_per_s"] = 32 / (time.perf_counter() - t0)
+            single["pmu_se_cpu_vs_gpu_max_abs_difference"] = float(np.abs(xs - X[:32]).max())
+        except Exception as e:
+            single["pmu_se_error"] = str(e)
 
     if rank != 0:
         if world > 1:

@@ -8,6 +8,7 @@
 module JuliaGridB200
 
 using JuliaGrid
+using SparseArrays
 import JuliaGrid: newtonRaphson, gaussNewton, mismatch!, solve!, increment!, powerFlow!, stateEstimation!,
     setInitialPoint!, AC, Polar, PowerSystem, Measurement, Normal
 
@@ -192,6 +193,70 @@ function stateEstimation!(a::AcStateEstimationB200; iteration::Int64 = 40, toler
     return nothing
 end
 
-export B200
+# ---- linear analyses (DC power flow, DC and PMU state estimation): one device factorisation, many right-hand sides ----
+# The reference's own setup functions build every table (`dcPowerFlow`, `dcStateEstimation`, `pmuStateEstimation`
+# with the default LU tag); only `factorization / solution!` is replaced (src/backend/utility.jl:470-586).
+
+"Device LDLt of a symmetric SparseMatrixCSC; `skip` = slack index whose row/column becomes the identity (0: none)."
+mutable struct LinearB200
+    ctx::Ctx
+    n::Int64
+    m::Int64
+end
+
+function LinearB200(A::SparseMatrixCSC{Float64, Int64}; skip::Integer = 0, device::Integer = 0)
+    ctx = Ctx(device)
+    GC.@preserve A check(ctx, ccall((:jgb_lin_setup, libjgb), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Int64),
+        ctx.handle, size(A, 1), A.colptr, A.rowval, A.nzval, skip))
+    return LinearB200(ctx, size(A, 1), 0)
+end
+
+"P = precision * coefficient (m x n): right-hand sides are formed on the device as P' z."
+function projection!(F::LinearB200, P::SparseMatrixCSC{Float64, Int64})
+    GC.@preserve P check(F.ctx, ccall((:jgb_lin_projection, libjgb), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}), F.ctx.handle, size(P, 1), P.colptr, P.rowval, P.nzval))
+    F.m = size(P, 1)
+    return F
+end
+
+"`solution!` for every column of B (n x R, one right-hand side per column; Julia's column-major = the ABI's [R][n])."
+function solution(F::LinearB200, B::Matrix{Float64})
+    X = similar(B)
+    check(F.ctx, ccall((:jgb_lin_solve, libjgb), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}),
+        F.ctx.handle, size(B, 2), B, X))
+    return X
+end
+
+"x_r = A^-1 P' z_r for every column of Z (m x R, one measurement vector per Monte-Carlo draw)."
+function projectedSolution(F::LinearB200, Z::Matrix{Float64})
+    X = Matrix{Float64}(undef, F.n, size(Z, 2))
+    check(F.ctx, ccall((:jgb_lin_solve_projected, libjgb), Int32, (Ptr{Cvoid}, Int64, Ptr{Float64}, Ptr{Float64}),
+        F.ctx.handle, size(Z, 2), Z, X))
+    return X
+end
+
+"DC power flow angles for every column of `rhs` (pf.rhs per injection scenario, dcPowerFlow.jl:99-102)."
+function dcPowerFlowB200(system::PowerSystem, rhs::Matrix{Float64}; device::Integer = 0)
+    dc, slack = system.model.dc, system.bus.layout.slack
+    F = LinearB200(dc.nodalMatrix; skip = slack, device = device)
+    θ = solution(F, rhs)
+    θ[slack, :] .= 0.0                                  # addSlackAngle! (backend/utility.jl:610-622)
+    θ .+= system.bus.voltage.angle[slack]
+    return θ
+end
+
+"Linear WLS estimates for every column of Z: `se` is the `WLS` method of dcStateEstimation / pmuStateEstimation."
+function linearEstimationB200(se, Z::Matrix{Float64}; slack::Integer = 0, device::Integer = 0)
+    H = copy(se.coefficient)
+    slack > 0 && (H[:, slack] .= 0.0)                   # removeColumn (backend/sparse.jl:155-163)
+    P = se.precision * H
+    G = transpose(H) * P
+    slack > 0 && (G[slack, slack] = 1.0)
+    F = projection!(LinearB200(sparse((G + transpose(G)) / 2); skip = slack, device = device), P)
+    return projectedSolution(F, Z)
+end
+
+export B200, LinearB200, projection!, solution, projectedSolution, dcPowerFlowB200, linearEstimationB200
 
 end # module
