@@ -136,6 +136,18 @@ int32_t jgb_wls_batch_dev(jgb_ctx* ctx, int64_t S, const double* Z_dev, int64_t 
                           double* vm_out_dev, double* va_out_dev, int32_t* iterations_dev, int8_t* status_dev,
                           double* objective_dev, int64_t* total_iterations);
 
+/* ---- bad-data post-step -------------------------------------------------------------------------
+ * == the numeric part of residualTest!(analysis; threshold) for Gauss-Newton WLS (src/stateEstimation/badData.jl:181-285):
+ * c[i] = h_i G^-1 h_i' from a sparse selected inverse of the gain factor on the device (Takahashi recurrences on the
+ * elimination tree; `selectedInverse` / `rowProjection` badData.jl:287-362, 536-640), then the largest normalised
+ * residual |r_i| / sqrt|1/W_ii - c_i| over the rows with a non-zero residual. Call after jgb_wls_run / the last
+ * jgb_wls_increment. index: 1-based row, 0 if none; c_out: nullable [m]. */
+int32_t jgb_wls_residual_test(jgb_ctx* ctx, double threshold, double* max_normalized_residual, int64_t* index,
+                              double* c_out);
+/* Row `row` (1-based) leaves the model as in badData.jl:258-282: H entries, mean and residual zeroed, type 0,
+ * iteration 0 (the monitoring-side status bookkeeping stays with the caller). */
+int32_t jgb_wls_remove_row(jgb_ctx* ctx, int64_t row);
+
 /* ---- constant-matrix linear solves -------------------------------------------------------------
  * The reference's linear analyses factor one sparse symmetric matrix and call `solution!` per right-hand side:
  *   DC power flow      solve!  src/powerFlow/dcPowerFlow.jl:93-134        (B theta = P, slack row/column -> identity)

@@ -10,7 +10,8 @@ from .ac_power_flow import (AcPowerFlow, newton_raphson, mismatch, solve, power_
 from .measurement import (Measurement, measurement, power, add_voltmeter, add_ammeter, add_wattmeter,  # noqa: F401
                           add_varmeter, add_pmu, ac_wls, WlsTables)
 from .ac_state_estimation import (AcStateEstimation, gauss_newton, increment, solve_se, state_estimation,  # noqa: F401
-                                  set_mean, set_voltage_se, gaussNewton, stateEstimation)
+                                  set_mean, set_voltage_se, gaussNewton, stateEstimation, chi_test,
+                                  residual_test, ChiTest, ResidualTest, chiTest, residualTest)
 from .batch import BatchResult, eligible_outages, outage_arrays, nr_batch, wls_batch  # noqa: F401
 from .linear_solver import LinearSolver  # noqa: F401
 from .dc_power_flow import DcModel, DcPowerFlow, dc_model, dc_power_flow, solve_dc, dc_batch, power_dc  # noqa: F401

@@ -65,6 +65,8 @@ WLS_PROTOTYPES = {
     "jgb_wls_run": (C.c_int32, [C.c_void_p, C.c_int64, C.c_double, c_i64p, c_f64p, c_f64p]),
     "jgb_wls_batch": (C.c_int32, [C.c_void_p, C.c_int64, c_f64p, C.c_int64, C.c_double, c_f64p, c_f64p, c_i32p,
                                   c_i8p, c_f64p, c_i64p]),
+    "jgb_wls_residual_test": (C.c_int32, [C.c_void_p, C.c_double, c_f64p, c_i64p, c_f64p]),
+    "jgb_wls_remove_row": (C.c_int32, [C.c_void_p, C.c_int64]),
     "jgb_wls_batch_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]),
 }

@@ -5,6 +5,8 @@
     solve_se(analysis)               <-> solve!(analysis)                :1035-1047
     state_estimation(analysis; ...)  <-> stateEstimation!(analysis; ...) :1286-1329
     set_mean(analysis, z)            <-> update*!(analysis; ...) value updates (measurement/*.jl), pattern fixed
+    chi_test(analysis)               <-> chiTest(analysis)               src/stateEstimation/badData.jl (chi-square part)
+    residual_test(analysis)          <-> residualTest!(analysis)         src/stateEstimation/badData.jl:181-285
 """
 from __future__ import annotations
 
@@ -142,5 +144,81 @@ def set_voltage_se(a: AcStateEstimation, magnitude, angle):
     a._dirty = True
 
 
+class ChiTest:
+    def __init__(self, detect, threshold, objective):
+        self.detect, self.threshold, self.objective = detect, threshold, objective
+
+
+def chi_test(a: AcStateEstimation, confidence: float = 0.95) -> ChiTest:
+    """chiTest(analysis; confidence): WLS objective against the chi-square quantile, m_in_service - (2n - 1) dof."""
+    import scipy.stats
+    dof = int(np.count_nonzero(a.method.type)) - (2 * a.system.n - 1)
+    thr = float(scipy.stats.chi2.ppf(confidence, dof))
+    return ChiTest(a.method.objective > thr, thr, a.method.objective)
+
+
+class ResidualTest:
+    """bad = ResidualTest(detect, maxNormalizedResidual, label, index) (src/definition/analysis.jl); `label` is
+    (device class, 0-based device index) here — labels are a host-side naming layer of the reference."""
+
+    def __init__(self, detect, max_normalized_residual, label, index):
+        self.detect, self.maxNormalizedResidual, self.label, self.index = detect, max_normalized_residual, label, index
+
+
+def residual_test(a: AcStateEstimation, threshold: float = 3.0) -> ResidualTest:
+    """residualTest!(analysis; threshold): numeric part on the device (selected inverse of the gain factor, row
+    projection), status bookkeeping of badData.jl:224-282 here. index is the 0-based row, -1 when none."""
+    rn, idx = C.c_double(0), C.c_int64(0)
+    a.ctx.check(a.ctx.lib.jgb_wls_residual_test(a.ctx.handle, threshold, C.byref(rn), C.byref(idx), None))
+    me, mon = a.method, a.monitoring
+    row = idx.value - 1
+    detect = rn.value > threshold
+    label = None
+    if row >= 0:
+        r = me.range - 1                       # 0-based block starts: volt | amp | watt | var | pmu
+        nv, na, nw, nq = (len(getattr(mon, d)["index"]) for d in ("volt", "amp", "watt", "var"))
+        rows = [row]
+        if row < r[1]:
+            label = ("voltmeter", row)
+            if detect:
+                mon.volt["status"][row] = 0
+        elif row < r[2]:
+            label = ("ammeter", row - nv)
+            if detect:
+                mon.amp["status"][row - nv] = 0
+        elif row < r[3]:
+            label = ("wattmeter", row - nv - na)
+            if detect:
+                mon.watt["status"][row - nv - na] = 0
+        elif row < r[4]:
+            label = ("varmeter", row - nv - na - nw)
+            if detect:
+                mon.var["status"][row - nv - na - nw] = 0
+        else:
+            local = row - nv - na - nw - nq
+            k = local // 2
+            label = ("pmu", k)
+            if detect:
+                if mon.pmu["polar"][k]:
+                    if int(me.type[row]) in (2, 3, 4, 5, 12):
+                        mon.pmu["mag_status"][k] = 0
+                    else:
+                        mon.pmu["ang_status"][k] = 0
+                else:
+                    mon.pmu["mag_status"][k] = 0
+                    mon.pmu["ang_status"][k] = 0
+                    rows.append(row + 1 if local % 2 == 0 else row - 1)
+        if detect:
+            me.type = np.array(me.type, copy=True)
+            for q in rows:
+                a.ctx.check(a.ctx.lib.jgb_wls_remove_row(a.ctx.handle, q + 1))
+                me.mean[q] = 0.0
+                me.type[q] = 0
+            me.iteration = 0
+    return ResidualTest(detect, rn.value, label, row)
+
+
 gaussNewton = gauss_newton
+chiTest = chi_test
+residualTest = residual_test
 stateEstimation = state_estimation

@@ -341,6 +341,17 @@ int32_t jgb_profile(jgb_ctx* ctx, int32_t enable) {
     });
 }
 
+#ifdef JGB_WITH_WLS
+int32_t jgb_wls_residual_test(jgb_ctx* ctx, double threshold, double* max_normalized_residual, int64_t* index,
+                              double* c_out) {
+    return guarded(ctx, [&] { wls_of(ctx).residual_test(threshold, max_normalized_residual, index, c_out); return 0; });
+}
+
+int32_t jgb_wls_remove_row(jgb_ctx* ctx, int64_t row) {
+    return guarded(ctx, [&] { wls_of(ctx).remove_row(row); return 0; });
+}
+#endif
+
 int32_t jgb_lin_setup(jgb_ctx* ctx, int64_t n, const int64_t* a_colptr, const int64_t* a_rowval, const double* a_nzval,
                       int64_t skip) {
     return guarded(ctx, [&] {

@@ -812,6 +812,62 @@ mf_bwd_multi_kernel(DevSym sy, const int* __restrict__ fronts, const double* __r
     for (int p = e; p < k; p += TE) B[(long long)rows[p] * R + r] = t[p * 32];
 }
 
+// ---- sparse selected inverse on the elimination tree (symmetric matrices, S == 1) --------------------------------
+// Takahashi recurrences per front, roots first: with the front's index set I = [pivots | update rows], Z = A^-1 on
+// I x I is obtained from the parent's block (the update rows are a subset of the parent's index set) and, for the
+// pivots p = k-1 .. 0,   Z[j,p] = -sum_{l>p} Z[j,l] L[l,p]  (j > p),   Z[p,p] = 1/d_p - sum_{l>p} Z[p,l] L[l,p],
+// with L[l,p] = U[p,l] / d_p read from the packed U rows. Every front keeps its full nf x nf block (column major) in Z
+// at zoff[f]; the entries of A^-1 on the pattern of L + L' are exactly the union of these blocks. One CTA per front,
+// the block lives in global memory (L2) because the largest fronts exceed shared memory; this is a one-off post-step
+// (largest normalised residual, badData.jl:181-285), not part of the iteration loop.
+__global__ void __launch_bounds__(256)
+mf_selinv_kernel(DevSym sy, const int* __restrict__ fronts, const int* __restrict__ parent,
+                 const double* __restrict__ U, double* __restrict__ Z, const long long* __restrict__ zoff) {
+    extern __shared__ double sh[];          // lvec[nf] | zcol[nf]
+    __shared__ double s_diag;
+    const int f = fronts[blockIdx.x];
+    const int nf = sy.f_nf[f], k = sy.f_k[f], u = nf - k;
+    double* lvec = sh;
+    double* zcol = sh + nf;
+    double* __restrict__ Zf = Z + zoff[f];
+    const int pf = parent[f];
+    if (pf >= 0) {
+        const int nfp = sy.f_nf[pf];
+        const double* __restrict__ Zp = Z + zoff[pf];
+        const int* __restrict__ rel = sy.f_rel + sy.f_relptr[f];
+        for (int t = threadIdx.x; t < u * u; t += blockDim.x) {
+            const int a = t % u, b = t / u;
+            Zf[(k + a) + (long long)(k + b) * nf] = Zp[rel[a] + (long long)rel[b] * nfp];
+        }
+    }
+    __syncthreads();
+    const double* __restrict__ Uf = U + sy.f_uoff[f];
+    for (int p = k - 1; p >= 0; --p) {
+        const double* __restrict__ Urow = Uf + urow_off(p, nf);
+        const double inv = Urow[0];
+        for (int l = p + 1 + threadIdx.x; l < nf; l += blockDim.x) lvec[l] = Urow[l - p] * inv;
+        __syncthreads();
+        for (int j = p + 1 + threadIdx.x; j < nf; j += blockDim.x) {
+            double acc = 0.0;
+            for (int l = p + 1; l < nf; ++l) acc += Zf[j + (long long)l * nf] * lvec[l];
+            zcol[j] = -acc;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double acc = inv;
+            for (int l = p + 1; l < nf; ++l) acc -= zcol[l] * lvec[l];
+            s_diag = acc;
+        }
+        for (int j = p + 1 + threadIdx.x; j < nf; j += blockDim.x) {
+            Zf[j + (long long)p * nf] = zcol[j];
+            Zf[p + (long long)j * nf] = zcol[j];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) Zf[p + (long long)p * nf] = s_diag;
+        __syncthreads();
+    }
+}
+
 constexpr int kMaxSmemFront = 150;    // nf*(nf+1)*8 bytes must fit the 200 KB dynamic shared-memory budget
 
 int pow2_floor(int v) {
@@ -827,6 +883,7 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
     symmetric = symmetric_matrix;
     d_coff.release();
     csum = 0;
+    d_zoff.release();
     d_f_k.upload(sym.f_k, st);
     d_f_nf.upload(sym.f_nf, st);
     d_f_rowptr.upload(sym.f_rowptr, st);
@@ -1135,6 +1192,29 @@ void MfSolver::solve_multi(double* B, int R, cudaStream_t st) {
         mf_bwd_multi_kernel<<<dim3(e - b, R / 32), threads, smem, st>>>(dev, d_depth_fronts.p + b, d_U.p, B, R);
     }
     JGB_CUDA(cudaGetLastError());
+}
+
+const double* MfSolver::selected_inverse(cudaStream_t st) {
+    if (!symmetric) throw std::logic_error("selected_inverse needs a symmetric matrix");
+    if (planned_S != 1) throw std::logic_error("selected_inverse: factor the matrix (S = 1) first");
+    if (d_zoff.n == 0) {
+        zoff_host.assign(sym.nfronts + 1, 0);
+        for (int f = 0; f < sym.nfronts; ++f)
+            zoff_host[f + 1] = zoff_host[f] + (long long)sym.f_nf[f] * sym.f_nf[f];
+        d_zoff.upload(zoff_host, st);
+        d_parent.upload(sym.f_parent, st);
+        JGB_CUDA(cudaStreamSynchronize(st));
+        d_Zinv.alloc((size_t)zoff_host[sym.nfronts]);
+    }
+    for (int d = 0; d < sym.ndepths; ++d) {
+        const int b = sym.depthptr[d], e = sym.depthptr[d + 1];
+        int mx = 0;
+        for (int q = b; q < e; ++q) mx = std::max(mx, sym.f_nf[sym.depth_fronts[q]]);
+        mf_selinv_kernel<<<e - b, 256, 2 * (size_t)mx * sizeof(double), st>>>(dev, d_depth_fronts.p + b, d_parent.p,
+                                                                              d_U.p, d_Zinv.p, d_zoff.p);
+    }
+    JGB_CUDA(cudaGetLastError());
+    return d_Zinv.p;
 }
 
 }  // namespace jgb

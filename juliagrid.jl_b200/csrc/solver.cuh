@@ -69,6 +69,12 @@ class MfSolver {
     // stored factor (`solution!` per draw in the reference, utility.jl:576-586). B is [n][R] (entry i of column r at
     // B[i * R + r], R a multiple of 32) and is overwritten by X.
     void solve_multi(double* B, int R, cudaStream_t st);
+    // After a factor_solve with S == 1 of a symmetric matrix: the entries of A^-1 on the pattern of L + L' (sparse
+    // selected inverse, what the reference takes from `sparseinv` / Takahashi on the CHOLMOD factor,
+    // stateEstimation/badData.jl:330-347, 536-640). Returns the device array; front f holds its nf x nf block (column
+    // major, rows / columns in f_rows order) at zoff_host[f].
+    const double* selected_inverse(cudaStream_t st);
+    std::vector<long long> zoff_host;
     int64_t factor_bytes(int S) const;     // algorithmic HBM bytes of one factor_solve (for roofline reports)
     int launches_per_solve(int S);
     int factor_launches(int S) { plan(S); return (int)fplan.size(); }
@@ -83,7 +89,9 @@ class MfSolver {
         d_asm_src, d_asm_dst, d_level_fronts, d_depth_fronts, d_f_eaptr, d_ea_roundptr, d_ea_pair;
     DevBuf<long long> d_f_uoff, d_f_updoff;
     DevBuf<double> d_U, d_upd, d_gwork, d_cvec;
-    DevBuf<long long> d_coff;
+    DevBuf<long long> d_coff, d_zoff;
+    DevBuf<double> d_Zinv;
+    DevBuf<int> d_parent;
     long long csum = 0;
     DevBuf<FrontDesc> d_level_desc;
     DevBuf<ChildDesc> d_child_desc;

@@ -449,6 +449,33 @@ __global__ void wls_copy_results_kernel(const int* __restrict__ iters, const int
 
 }  // namespace
 
+// ---- bad-data post-step: c[i] = h_i G^-1 h_i' from the selected inverse of the gain factor ----
+// rowProjection (stateEstimation/badData.jl:349-362, 477-499). One thread per measurement row; its pairs of H entries
+// (a <= b in slot order, slack column skipped) and the offsets of (G^-1)[a,b] inside the per-front blocks of the
+// selected inverse were listed on the host; fixed order, no atomics.
+__global__ void wls_projection_kernel(int m, const int* __restrict__ pair_ptr, const int* __restrict__ pair_pa,
+                                      const int* __restrict__ pair_pb, const long long* __restrict__ pair_z,
+                                      const double* __restrict__ hval, const double* __restrict__ Z,
+                                      double* __restrict__ c) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= m) return;
+    double acc = 0.0;
+    for (int t = pair_ptr[row]; t < pair_ptr[row + 1]; ++t) {
+        const int pa = pair_pa[t], pb = pair_pb[t];
+        const double v = hval[pa] * hval[pb] * Z[pair_z[t]];
+        acc += (pa == pb) ? v : 2.0 * v;
+    }
+    c[row] = acc;
+}
+
+// residualTest! bookkeeping on the device (badData.jl:258-282): the row leaves the model — H entries, mean and
+// residual zeroed, type 0.
+__global__ void wls_remove_row_kernel(int row, const int* __restrict__ slotpos, int s0, int s1, double* hval,
+                                      double* res, double* z, signed char* type) {
+    for (int t = s0 + threadIdx.x; t < s1; t += blockDim.x) hval[slotpos[t]] = 0.0;
+    if (threadIdx.x == 0) { res[row] = 0.0; z[row] = 0.0; type[row] = 0; }
+}
+
 void WlsContext::setup(int64_t n_, int64_t m_, int64_t slack_, const int64_t* hcp, const int64_t* hrv,
                        const int8_t* type, const int64_t* index, const int64_t* range6, const int64_t* wcp,
                        const int64_t* wrv, const double* wnz, const int64_t* ycp, const int64_t* yrv,
@@ -646,6 +673,14 @@ void WlsContext::setup(int64_t n_, int64_t m_, int64_t slack_, const int64_t* hc
     iteration = 0;
     have_mean = have_state = false;
     batch_S = 0;
+    // host copies for the lazily built bad-data lists (residual_test)
+    h_slotptr = slotptr;
+    h_slotpos = slotpos;
+    h_wdiag = wdiag;
+    h_poscol.assign(nnzh, 0);
+    for (int c = 0; c < nv; ++c)
+        for (int q = hcolptr[c]; q < hcolptr[c + 1]; ++q) h_poscol[q] = c;
+    have_pairs = false;
 }
 
 void WlsContext::set_mean(const double* z) {
@@ -927,6 +962,94 @@ double WlsContext::stat(const std::string& key) {
     if (key == "wls.gain_bytes") return 12.0 * nnzh + 8.0 * m + 8.0 * nnzg + 16.0 * n;
     if (key == "wls.solve_bytes") return (double)solver.factor_bytes(1);
     return -1.0;
+}
+
+void WlsContext::build_pairs() {
+    const Symbolic& sy = solver.sym;
+    const int nv = 2 * n;
+    // pivot owner of every variable and, per front, its rows sorted by variable id for local-index lookups
+    std::vector<int> owner(nv, -1);
+    std::vector<std::vector<std::pair<int, int>>> local(sy.nfronts);
+    for (int f = 0; f < sy.nfronts; ++f) {
+        const int* rows = sy.f_rows.data() + sy.f_rowptr[f];
+        for (int q = 0; q < sy.f_k[f]; ++q) owner[rows[q]] = f;
+        local[f].reserve(sy.f_nf[f]);
+        for (int q = 0; q < sy.f_nf[f]; ++q) local[f].push_back({rows[q], q});
+        std::sort(local[f].begin(), local[f].end());
+    }
+    auto find_local = [&](int f, int var) -> int {
+        auto it = std::lower_bound(local[f].begin(), local[f].end(), std::make_pair(var, -1));
+        if (it == local[f].end() || it->first != var)
+            throw std::runtime_error("bad-data lists: a gain entry is missing from the factor pattern (-4)");
+        return it->second;
+    };
+    solver.selected_inverse(stream);          // allocates the blocks and fills zoff_host
+    std::vector<int> pptr(m + 1, 0), ppa, ppb;
+    std::vector<long long> pz;
+    for (int r = 0; r < m; ++r) {
+        for (int x = h_slotptr[r]; x < h_slotptr[r + 1]; ++x) {
+            const int pa = h_slotpos[x], a = h_poscol[pa];
+            if (a == slack) continue;
+            for (int y = x; y < h_slotptr[r + 1]; ++y) {
+                const int pb = h_slotpos[y], b = h_poscol[pb];
+                if (b == slack) continue;
+                const int first = sy.iperm[a] < sy.iperm[b] ? a : b;
+                const int f = owner[first];
+                const int nf = sy.f_nf[f];
+                ppa.push_back(pa);
+                ppb.push_back(pb);
+                pz.push_back(solver.zoff_host[f] + find_local(f, a) + (long long)find_local(f, b) * nf);
+            }
+        }
+        pptr[r + 1] = (int)ppa.size();
+    }
+    d_pair_ptr.upload(pptr, stream);
+    d_pair_pa.upload(ppa, stream);
+    d_pair_pb.upload(ppb, stream);
+    d_pair_z.upload(pz, stream);
+    d_proj.alloc(m);
+    JGB_CUDA(cudaStreamSynchronize(stream));
+    have_pairs = true;
+}
+
+void WlsContext::residual_test(double threshold, double* max_rn, int64_t* index, double* c_out) {
+    if (!have_mean || !have_state) throw std::logic_error("residual_test needs a solved estimation on the device");
+    (void)threshold;
+    if (!have_pairs) build_pairs();
+    // H, the residual and the gain factor on the device are those of the last increment! (final state)
+    const double* Z = solver.selected_inverse(stream);
+    wls_projection_kernel<<<ceil_div(m, 128), 128, 0, stream>>>(m, d_pair_ptr.p, d_pair_pa.p, d_pair_pb.p, d_pair_z.p,
+                                                               d_hval.p, Z, d_proj.p);
+    launches += 1 + solver.sym.ndepths;
+    JGB_CUDA(cudaGetLastError());
+    std::vector<double> c(m), res(m);
+    d_proj.download(c.data(), m, stream);
+    d_res.download(res.data(), m, stream);
+    JGB_CUDA(cudaStreamSynchronize(stream));
+    double best = 0.0;
+    int64_t where = 0;
+    for (int i = 0; i < m; ++i) {               // badData.jl:207-215: strict >, ascending rows
+        if (res[i] != 0.0) {
+            const double rn = std::fabs(res[i]) / std::sqrt(std::fabs(1.0 / h_wdiag[i] - c[i]));
+            if (rn > best) { best = rn; where = i + 1; }
+        }
+    }
+    if (max_rn) *max_rn = best;
+    if (index) *index = where;
+    if (c_out) std::copy(c.begin(), c.end(), c_out);
+}
+
+void WlsContext::remove_row(int64_t row1) {
+    if (!m) throw std::logic_error("wls_setup has not been called");
+    if (row1 < 1 || row1 > m) throw std::invalid_argument("wls_remove_row: row out of range");
+    const int r = (int)row1 - 1;
+    wls_remove_row_kernel<<<1, 32, 0, stream>>>(r, d_slotpos.p, h_slotptr[r], h_slotptr[r + 1], d_hval.p, d_res.p,
+                                               d_z.p, d_type.p);
+    ++launches;
+    for (int t = h_slotptr[r]; t < h_slotptr[r + 1]; ++t) h_const[h_slotpos[t]] = 0.0;
+    JGB_CUDA(cudaGetLastError());
+    JGB_CUDA(cudaStreamSynchronize(stream));
+    iteration = 0;
 }
 
 }  // namespace jgb

@@ -73,6 +73,10 @@ class WlsContext {
     int run(int64_t max_iter, double tol, int64_t* iters, double* max_inc, double* objective);
     int batch(int64_t S, const double* Z, bool dev_in, int64_t max_iter, double tol, double* vm_out, double* va_out,
               int32_t* iters, int8_t* status, double* objective, bool dev_out, int64_t* total);
+    // largest normalised residual (residualTest!, stateEstimation/badData.jl:181-285): the numeric part; the
+    // monitoring bookkeeping stays with the host. index is 1-based, 0 when every residual is zero.
+    void residual_test(double threshold, double* max_rn, int64_t* index, double* c_out);
+    void remove_row(int64_t row);              // 1-based; the row leaves the model (type 0)
     double stat(const std::string& key);
 
     int n = 0, m = 0, slack = -1, nnzh = 0, nnzg = 0, nbr = 0, nnzy = 0;
@@ -112,6 +116,14 @@ class WlsContext {
     PinnedBuf<int> h_i;
     int64_t iteration = 0;
     bool have_mean = false, have_state = false;
+    // bad-data lists (built on the first residual_test)
+    void build_pairs();
+    bool have_pairs = false;
+    std::vector<int> h_slotptr, h_slotpos, h_poscol;
+    std::vector<double> h_wdiag;
+    DevBuf<int> d_pair_ptr, d_pair_pa, d_pair_pb;
+    DevBuf<long long> d_pair_z;
+    DevBuf<double> d_proj;
 };
 
 }  // namespace jgb

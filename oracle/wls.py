@@ -604,3 +604,76 @@ def export_one_based(a: GaussNewton) -> dict:
         "index": (a.index + 1).astype(np.int64),
         "range": (a.range + 1).astype(np.int64),
     }
+
+
+# ----------------------------------------------------------------------------- bad data
+def chi_test(a: GaussNewton, confidence: float = 0.95):
+    """chiTest (stateEstimation/badData.jl:1-46 of the chi-square part): objective against the chi2 quantile with
+    m_in_service - (2n - 1) degrees of freedom."""
+    import scipy.stats
+    inservice = int(np.count_nonzero(a.type))
+    threshold = scipy.stats.chi2.ppf(confidence, inservice - (2 * a.sys.n - 1))
+    return a.objective > threshold, threshold, a.objective
+
+
+def residual_projection(a: GaussNewton) -> np.ndarray:
+    """c[i] = h_i G^-1 h_i' with the slack column of H removed and G[slack, slack] = 1
+    (residualTest!, badData.jl:198-203; badDataProjection / rowProjection, :287-362). The reference reads the entries
+    of G^-1 it needs from a sparse selected inverse of the gain factor; here they come from SuperLU solves."""
+    n = a.sys.n
+    H = a.jacobian().tolil()
+    H[:, a.slack] = 0.0
+    H = H.tocsc()
+    G = (H.T @ a.w @ H).tolil()
+    G[a.slack, a.slack] = 1.0
+    lu = spla.splu(G.tocsc())
+    X = lu.solve(H.T.toarray())                 # G^-1 H'   (2n x m), dense: small / medium cases only
+    return np.asarray(H.multiply(X.T).sum(axis=1)).ravel()
+
+
+def residual_projection_rows(a: GaussNewton, rows) -> np.ndarray:
+    """Same quantity for a sample of rows (large cases): one SuperLU solve per row."""
+    H = a.jacobian().tolil()
+    H[:, a.slack] = 0.0
+    H = H.tocsr()
+    G = (H.T @ a.w @ H).tolil()
+    G[a.slack, a.slack] = 1.0
+    lu = spla.splu(G.tocsc())
+    out = np.zeros(len(rows))
+    for q, r in enumerate(rows):
+        h = H.getrow(int(r)).toarray().ravel()
+        out[q] = h @ lu.solve(h)
+    return out
+
+
+def residual_test(a: GaussNewton, threshold: float = 3.0):
+    """residualTest! for Gauss-Newton WLS (badData.jl:181-285). Returns (detect, max normalised residual, row index
+    or -1); on detection the row (and its partner for a rectangular PMU) is taken out of service exactly like the
+    reference: H row, mean and residual zeroed, type 0, iteration 0."""
+    c = residual_projection(a)
+    wdiag = a.w.diagonal()
+    best, index = 0.0, -1
+    for i in range(a.m):
+        if a.residual[i] != 0.0:
+            rn = abs(a.residual[i]) / sqrt(abs(1 / wdiag[i] - c[i]))
+            if rn > best:
+                best, index = rn, i
+    detect = best > threshold
+    if detect:
+        rows = [index]
+        if index >= a.range[4]:                               # PMU block: rectangular pairs go together
+            code = int(a.type[index])
+            if code in (16, 17, 18, 19, 20, 21):
+                local = index - a.range[4]
+                rows.append(index - 1 if local % 2 == 1 else index + 1)
+        for r in rows:
+            for col in range(2 * a.sys.n):
+                lo, hi = a.h_colptr[col], a.h_colptr[col + 1]
+                k = lo + int(np.searchsorted(a.h_rowval[lo:hi], r))
+                if k < hi and a.h_rowval[k] == r:
+                    a.h_nzval[k] = 0.0
+            a.mean[r] = 0.0
+            a.residual[r] = 0.0
+            a.type[r] = 0
+        a.iteration = 0
+    return detect, best, index

@@ -136,3 +136,44 @@ def test_outage_reuse_matches_rebuild():
     np.testing.assert_allclose(a1.vm, a2.vm, atol=1e-8)
     np.testing.assert_allclose(a1.va, a2.va, atol=1e-8)
     assert np.array_equal(a1.j_rowval, a2.j_rowval)
+
+
+def _bad_data_case(two_outliers):
+    """Setups of test/stateEstimation/badData.jl:5-41 (one outlier) and :58-84 (two outliers)."""
+    s = oracle_system("case14test")
+    s.bus_type[0] = 2
+    s.bus_type[2] = 3
+    s.slack = 2
+    s.va[2] = -0.17
+    a = nr.newton_raphson(s)
+    assert nr.power_flow(a)
+    pw = post.powers(s, a.mdl, a.vm, a.va)
+    kw = dict(pmu_bus=range(s.n), pmu_polar=True, var_pmu_mag=1e-5, var_pmu_ang=1e-5) if two_outliers else {}
+    me = wls.measurements_from_solution(s, pw, a.vm, a.va, var_volt=1e-2, var_power=1e-2, **kw)
+    me.var["mean"][3] = 10.25                    # "Varmeter 4"
+    if two_outliers:
+        me.pmu["mag_mean"][9] = 30.0             # "PMU 10"
+    return s, a, me
+
+
+def test_bad_data_largest_normalized_residual_known_answers():
+    """residualTest!: 52.5 (Varmeter 4), then recovery; two outliers: 7713.26 (PMU 10), 78.3 (Varmeter 4), recovery
+    (test/stateEstimation/badData.jl:24-41, 58-84; all atol 1e-1, recovery 1e-10)."""
+    s, a, me = _bad_data_case(False)
+    se = wls.gauss_newton(s, me, a.mdl)
+    assert wls.state_estimation(se)
+    detect, rn, idx = wls.residual_test(se)
+    assert detect and abs(rn - 52.5) < 0.1 and idx == se.range[3] + 3
+    assert wls.state_estimation(se)
+    assert np.abs(se.vm - a.vm).max() < 1e-10 and np.abs(se.va - a.va).max() < 1e-10
+
+    s, a, me = _bad_data_case(True)
+    se = wls.gauss_newton(s, me, a.mdl)
+    assert wls.state_estimation(se)
+    detect, rn, idx = wls.residual_test(se)
+    assert detect and abs(rn - 7713.26) < 0.1 and idx == se.range[4] + 2 * 9
+    assert wls.state_estimation(se)
+    detect, rn, idx = wls.residual_test(se)
+    assert detect and abs(rn - 78.3) < 0.1 and idx == se.range[3] + 3
+    assert wls.state_estimation(se)
+    assert np.abs(se.vm - a.vm).max() < 1e-10 and np.abs(se.va - a.va).max() < 1e-10
