@@ -353,6 +353,14 @@ def run_ours(args):
             single["wls_single_case_gn_iterations_per_s"] = it_sum / (time.perf_counter() - t0)
             single["wls_single_case_iterations"] = se.method.iteration
             single["wls_rows"] = int(t.m)
+            # largest normalised residual (selected inverse of the gain factor + row projection)
+            jgb200.residual_test(se, threshold=1e300)          # builds the lists; threshold never met: nothing removed
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            rt = jgb200.residual_test(se, threshold=1e300)
+            torch.cuda.synchronize()
+            single["wls_residual_test_ms"] = (time.perf_counter() - t0) * 1e3
+            single["wls_max_normalized_residual"] = rt.maxNormalizedResidual
             # configs[4]-style Monte-Carlo batch: 256 noise draws of the same measurement set on this GPU
             Sm = 256
             Z = np.stack([t.mean + np.sqrt(1 / wd) * np.random.default_rng(1000 + q).standard_normal(t.m)

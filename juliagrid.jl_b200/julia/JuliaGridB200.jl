@@ -193,6 +193,56 @@ function stateEstimation!(a::AcStateEstimationB200; iteration::Int64 = 40, toler
     return nothing
 end
 
+"""
+    residualTest!(analysis::AcStateEstimationB200; threshold = 3.0)
+
+Largest normalised residual on the device (selected inverse of the gain factor + row projection); the device returns
+the 1-based row, the label / status bookkeeping below is JuliaGrid's own (stateEstimation/badData.jl:224-282).
+"""
+function JuliaGrid.residualTest!(a::AcStateEstimationB200; threshold::Float64 = 3.0)
+    ctx, se, mon = a.method.ctx, a.method, a.monitoring
+    rn, idx = Ref{Float64}(0), Ref{Int64}(0)
+    check(ctx, ccall((:jgb_wls_residual_test, libjgb), Int32, (Ptr{Cvoid}, Float64, Ref{Float64}, Ref{Int64}, Ptr{Float64}),
+        ctx.handle, threshold, rn, idx, C_NULL))
+    bad = JuliaGrid.ResidualTest(rn[] > threshold, rn[], "", idx[])
+    bad.index == 0 && return bad
+    nv, na, nw, nq = mon.voltmeter.number, mon.ammeter.number, mon.wattmeter.number, mon.varmeter.number
+    rows = [bad.index]
+    if bad.index < se.range[2]
+        bad.label, k = JuliaGrid.getLabelIdx(mon.voltmeter.label, bad.index)
+        bad.detect && (mon.voltmeter.magnitude.status[k] = 0)
+    elseif bad.index < se.range[3]
+        bad.label, k = JuliaGrid.getLabelIdx(mon.ammeter.label, bad.index - nv)
+        bad.detect && (mon.ammeter.magnitude.status[k] = 0)
+    elseif bad.index < se.range[4]
+        bad.label, k = JuliaGrid.getLabelIdx(mon.wattmeter.label, bad.index - nv - na)
+        bad.detect && (mon.wattmeter.active.status[k] = 0)
+    elseif bad.index < se.range[5]
+        bad.label, k = JuliaGrid.getLabelIdx(mon.varmeter.label, bad.index - nv - na - nw)
+        bad.detect && (mon.varmeter.reactive.status[k] = 0)
+    else
+        loc = bad.index - nv - na - nw - nq
+        bad.label, k = JuliaGrid.getLabelIdx(mon.pmu.label, (loc + 1) ÷ 2)
+        if bad.detect
+            if mon.pmu.layout.polar[k]
+                se.type[bad.index] in (2, 3, 4, 5, 12) ? (mon.pmu.magnitude.status[k] = 0) : (mon.pmu.angle.status[k] = 0)
+            else
+                mon.pmu.magnitude.status[k] = mon.pmu.angle.status[k] = 0
+                push!(rows, iseven(loc) ? bad.index - 1 : bad.index + 1)
+            end
+        end
+    end
+    if bad.detect
+        for r in rows
+            check(ctx, ccall((:jgb_wls_remove_row, libjgb), Int32, (Ptr{Cvoid}, Int64), ctx.handle, r))
+            se.mean[r] = 0.0
+            se.type[r] = 0
+        end
+        se.iteration = 0
+    end
+    return bad
+end
+
 # ---- linear analyses (DC power flow, DC and PMU state estimation): one device factorisation, many right-hand sides ----
 # The reference's own setup functions build every table (`dcPowerFlow`, `dcStateEstimation`, `pmuStateEstimation`
 # with the default LU tag); only `factorization / solution!` is replaced (src/backend/utility.jl:470-586).
