@@ -446,7 +446,12 @@ def run_ours(args):
     tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
     if os.path.exists(tp):
         with open(tp) as fh:
-            traffic = json.load(fh).get("mf_factor_kernel_dram_bytes_per_factor_phase")
+            tj = json.load(fh)
+            # ncu DRAM bytes of the factor launches of one iteration, measured at tj["scenarios"] scenarios; the
+            # traffic is per scenario (no cross-scenario reuse), so it scales linearly to this run's batch
+            traffic = tj.get("mf_factor_kernel_dram_bytes_per_factor_phase")
+            if traffic is not None and tj.get("scenarios"):
+                traffic = traffic * (S / float(tj["scenarios"]))
     roofline = {"bound": "hbm", "kernel": "mf_factor_kernel (all launches of one factor phase)", "achieved": achieved,
                 "peak": hbm, "peak_source": which, "unit": "GB/s", "frac": achieved / hbm, "traffic": traffic,
                 "algorithmic_bytes_per_phase": bytes_fac, "launches_per_phase": fac_launches,
@@ -484,7 +489,8 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--scenarios", type=int, default=4096, help="outage scenarios per GPU per step")
+    ap.add_argument("--scenarios", type=int, default=10000,
+                    help="outage scenarios per GPU per step (default: the whole 10 000-outage sweep of configs[3])")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

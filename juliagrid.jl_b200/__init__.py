@@ -6,7 +6,8 @@ from ._lib import Context, JgbError, load, LIB_PATH, exported_symbols  # noqa: F
 from .cases import PowerSystem, power_system, synthetic_grid  # noqa: F401
 from .model import AcModel, ac_model  # noqa: F401
 from .ac_power_flow import (AcPowerFlow, newton_raphson, mismatch, solve, power_flow, set_initial_point,  # noqa: F401
-                            set_voltage, update_branch, power_device, newtonRaphson, powerFlow, setInitialPoint, updateBranch)
+                            set_voltage, update_branch, power_device, newtonRaphson, powerFlow, setInitialPoint, updateBranch,
+                            generator_power, reactive_limit, adjust_angle, generatorPower, reactiveLimit, adjustAngle)
 from .measurement import (Measurement, measurement, power, add_voltmeter, add_ammeter, add_wattmeter,  # noqa: F401
                           add_varmeter, add_pmu, ac_wls, WlsTables)
 from .ac_state_estimation import (AcStateEstimation, gauss_newton, increment, solve_se, state_estimation,  # noqa: F401

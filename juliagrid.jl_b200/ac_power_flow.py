@@ -192,6 +192,82 @@ def power_device(a: AcPowerFlow) -> dict:
     return out
 
 
+def generator_power(a: AcPowerFlow, pw: dict | None = None):
+    """generatorPower for every generator (postprocessing/acAnalysis.jl:538-629) from the device's bus injections:
+    returns (active, reactive). A bus's reactive output is shared between its in-service generators in proportion
+    to their capability ranges; the first generator of the slack bus takes the active balance."""
+    s = a.system
+    pw = pw or power_device(a)
+    inj_p, inj_q = pw["injection_active"], pw["injection_reactive"]
+    on = np.flatnonzero(s.gen_status == 1)
+    pg, qg = np.zeros(s.ngen), np.zeros(s.ngen)
+    by_bus = {}
+    for g in on:
+        by_bus.setdefault(int(s.gen_bus[g]), []).append(int(g))
+    eps = np.finfo(float).eps
+    for b, gens in by_bus.items():
+        qsum = inj_q[b] + s.qd[b]
+        if len(gens) == 1:
+            g = gens[0]
+            pg[g] = inj_p[b] + s.pd[b] if b == a.slack else s.gen_p[g]
+            qg[g] = qsum
+            continue
+        qmin, qmax = s.gen_qmin[gens].copy(), s.gen_qmax[gens].copy()
+        fin_min, fin_max = qmin[~np.isinf(qmin)].sum(), qmax[~np.isinf(qmax)].sum()
+        big = abs(qsum) + abs(fin_min) + abs(fin_max)
+        qmin = np.where(np.isinf(qmin), np.where(qmin > 0, big, -big), qmin)
+        qmax = np.where(np.isinf(qmax), np.where(qmax < 0, -big, big), qmax)
+        smin, smax = qmin.sum(), qmax.sum()
+        if s.base_mva * abs(smin - smax) > 10 * eps:
+            qg[gens] = qmin + ((qsum - smin) / (smax - smin)) * (qmax - qmin)
+        else:
+            qg[gens] = qmin + (qsum - smin) / len(gens)
+        pg[gens] = s.gen_p[gens]
+        if b == a.slack:
+            pg[gens[0]] = inj_p[b] + s.pd[b] - s.gen_p[gens[1:]].sum()
+    return pg, qg
+
+
+def reactive_limit(a: AcPowerFlow) -> np.ndarray:
+    """reactiveLimit!(analysis) (acPowerFlow.jl:1081-1156). Mutates `a.system` like the reference: violating
+    generators are fixed at their limit and their bus becomes a demand bus (a converted slack hands over to the first
+    generator bus); returns the flags (-1 / +1). Build a new analysis with newton_raphson(system) afterwards."""
+    s = a.system
+    pg, qg = generator_power(a)
+    s.bus_type = a.bus_type.copy()
+    s.slack = a.slack
+    on = s.gen_status == 1
+    s.gen_p = np.where(on, pg, s.gen_p)
+    sp, sq = np.zeros(s.n), np.zeros(s.n)
+    np.add.at(sp, s.gen_bus[on], pg[on])
+    np.add.at(sq, s.gen_bus[on], qg[on])
+    violate = np.zeros(s.ngen, dtype=np.int64)
+    for i in np.flatnonzero(on & (s.gen_qmin < s.gen_qmax)):
+        j = int(s.gen_bus[i])
+        low, high = qg[i] < s.gen_qmin[i], qg[i] > s.gen_qmax[i]
+        if s.bus_type[j] != 1 and (low or high):
+            violate[i] = 1 if high else -1
+            new_q = s.gen_qmax[i] if high else s.gen_qmin[i]
+            s.bus_type[j] = 1
+            sq[j] += new_q - qg[i]
+            s.gen_q[i] = new_q
+            if j == s.slack:
+                cand = np.flatnonzero(s.bus_type == 2)
+                if len(cand):
+                    s.slack = int(cand[0])
+                    s.bus_type[s.slack] = 3
+    if s.bus_type[s.slack] != 3:
+        raise RuntimeError("The slack bus is missing.")
+    s.supply_p, s.supply_q = sp, sq
+    return violate
+
+
+def adjust_angle(a: AcPowerFlow, slack: int):
+    """adjustAngle!(analysis; slack) (acPowerFlow.jl:1186-1196); slack is a 0-based bus index."""
+    a.voltage.angle = a.voltage.angle + (a.system.va[slack] - a.voltage.angle[slack])
+    a._state_dirty = True
+
+
 def set_initial_point(a: AcPowerFlow):
     """setInitialPoint!(analysis): back to the start point of the constructor."""
     a.voltage = Polar(a._initial[0].copy(), a._initial[1].copy())
@@ -250,3 +326,9 @@ newtonRaphson = newton_raphson
 powerFlow = power_flow
 setInitialPoint = set_initial_point
 updateBranch = update_branch
+reactiveLimit = reactive_limit
+adjustAngle = adjust_angle
+generatorPower = generator_power
+reactiveLimit = reactive_limit
+adjustAngle = adjust_angle
+generatorPower = generator_power

@@ -44,6 +44,16 @@ class PowerSystem:
     base_mva: float = 100.0
     labels: list = field(default_factory=list)
     model: object = None      # system.model.ac once ac_model() ran
+    gen_qmin: np.ndarray = None   # generator.capability.minReactive (default -Inf)
+    gen_qmax: np.ndarray = None   # generator.capability.maxReactive (default +Inf)
+    supply_p: np.ndarray = None   # bus.supply.active / reactive once reactive_limit() rewrote them; None = derived from
+    supply_q: np.ndarray = None   # the in-service generators
+
+    def __post_init__(self):
+        if self.gen_qmin is None:
+            self.gen_qmin = np.full(self.ngen, -np.inf)
+        if self.gen_qmax is None:
+            self.gen_qmax = np.full(self.ngen, np.inf)
 
     def copy(self) -> "PowerSystem":
         return copy.deepcopy(self)
@@ -59,6 +69,8 @@ class PowerSystem:
         first = np.full(self.n, -1, dtype=np.int64)
         idx = np.flatnonzero(on)
         first[self.gen_bus[idx][::-1]] = idx[::-1]
+        if self.supply_p is not None:
+            return self.supply_p.copy(), self.supply_q.copy(), first
         return sp, sq, first
 
 
@@ -73,6 +85,11 @@ def _from_mapping(d) -> PowerSystem:
     for k in _FIELDS:
         dt = np.int8 if k in _I8 else np.int64 if k in _I64 else np.float64
         kw[k] = np.asarray(d[k], dtype=dt)
+    for k in ("gen_qmin", "gen_qmax"):
+        if k in d:          # JSON fixtures store +-Inf as null
+            sign = -1.0 if k == "gen_qmin" else 1.0
+            kw[k] = np.array([sign * np.inf if v is None else float(v) for v in np.asarray(d[k], dtype=object)],
+                             dtype=np.float64)
     return PowerSystem(n=int(d["n"]), slack=int(d["slack"]), nbr=int(d["nbr"]), ngen=int(d["ngen"]),
                        base_mva=float(d["base_mva"]),
                        labels=list(d["labels"]) if "labels" in d else list(range(1, int(d["n"]) + 1)), **kw)
@@ -116,7 +133,8 @@ def power_system(path: str) -> PowerSystem:
         r=br[:, 2].copy(), x=br[:, 3].copy(), g=np.zeros(len(br)), b=br[:, 4].copy(), tap=tap,
         shift=br[:, 9] * (np.pi / 180), status=br[:, 10].astype(np.int8),
         ngen=len(gen), gen_bus=look(gen[:, 0]).astype(np.int64), gen_p=gen[:, 1] * inv, gen_q=gen[:, 2] * inv,
-        gen_vm=gen[:, 5].copy(), gen_status=gen[:, 7].astype(np.int8), base_mva=base, labels=labels)
+        gen_vm=gen[:, 5].copy(), gen_status=gen[:, 7].astype(np.int8), base_mva=base, labels=labels,
+        gen_qmin=gen[:, 4] * inv, gen_qmax=gen[:, 3] * inv)
 
 
 def synthetic_grid(side: int = 100, seed: int = 20261017) -> PowerSystem:

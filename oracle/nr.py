@@ -274,3 +274,57 @@ def export_one_based(a: NewtonRaphson) -> dict:
         "j_colptr": (a.j_colptr + 1).astype(np.int64),
         "j_rowval": (a.j_rowval + 1).astype(np.int64),
     }
+
+
+def reactive_limit(a: NewtonRaphson) -> np.ndarray:
+    """reactiveLimit!(analysis) (acPowerFlow.jl:1081-1156): generators whose reactive output violates its capability
+    are fixed at the limit and their bus becomes a demand (PQ) bus; a converted slack bus hands the role to the
+    first generator (PV) bus. Mutates `a.sys` (types, slack, generator outputs, bus supply) like the reference
+    mutates `system`; returns the violation flags (-1 below minimum, +1 above maximum)."""
+    from .post import powers, generator_powers
+    sys = a.sys
+    sys.bus_type = a.bus_type.copy()          # the analysis' fix-ups live in system.bus.layout in the reference
+    sys.slack = a.slack
+    pw = powers(sys, a.mdl, a.vm, a.va)
+    pg, qg = generator_powers(sys, pw["injection_active"], pw["injection_reactive"], a.slack)
+    violate = np.zeros(sys.ngen, dtype=np.int64)
+    sys.supply_p[:] = 0.0
+    sys.supply_q[:] = 0.0
+    for k in range(sys.ngen):
+        if sys.gen_status[k] == 1:
+            b = int(sys.gen_bus[k])
+            sys.gen_p[k] = pg[k]
+            sys.supply_p[b] += pg[k]
+            sys.supply_q[b] += qg[k]
+    for i in range(sys.ngen):
+        if sys.gen_status[i] == 0:
+            continue
+        if sys.gen_qmin[i] < sys.gen_qmax[i]:
+            j = int(sys.gen_bus[i])
+            vmin = qg[i] < sys.gen_qmin[i]
+            vmax = qg[i] > sys.gen_qmax[i]
+            if sys.bus_type[j] != 1 and (vmin or vmax):
+                if vmin:
+                    violate[i] = -1
+                    new_q = sys.gen_qmin[i]
+                if vmax:
+                    violate[i] = 1
+                    new_q = sys.gen_qmax[i]
+                sys.bus_type[j] = 1
+                sys.supply_q[j] -= qg[i]
+                sys.gen_q[i] = new_q
+                sys.supply_q[j] += new_q
+                if j == sys.slack:
+                    for k in range(sys.n):
+                        if sys.bus_type[k] == 2:
+                            sys.slack = k
+                            sys.bus_type[k] = 3
+                            break
+    if sys.bus_type[sys.slack] != 3:
+        raise RuntimeError("The slack bus is missing.")
+    return violate
+
+
+def adjust_angle(a: NewtonRaphson, slack: int):
+    """adjustAngle!(analysis; slack) (acPowerFlow.jl:1186-1196)."""
+    a.va = a.va + (a.sys.va[slack] - a.va[slack])

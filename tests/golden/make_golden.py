@@ -50,6 +50,9 @@ def main(ref="/root/reference"):
         out["dcPowerFlow"] = {k: np.asarray(res[f"/{case}/dcPowerFlow/{k}"]).reshape(-1).tolist()
                               for k in res.keys(f"/{case}/dcPowerFlow")}
         out["source"] += f" + /{case}/dcPowerFlow"
+        rl = f"/{case}/reactiveLimit/newtonRaphson"
+        out["reactiveLimit"] = {k: np.asarray(res[rl + "/" + k]).reshape(-1).tolist() for k in res.keys(rl)}
+        out["source"] += f" + {rl}"
         with open(os.path.join(HERE, f"{case}.json"), "w") as fh:
             json.dump(out, fh)
         print(case, "iteration", out["newtonRaphson"]["iteration"])

@@ -182,3 +182,29 @@ def test_power_postprocessing_on_device(case, ctx):
                              ("from_active", "fromActive"), ("from_reactive", "fromReactive"),
                              ("to_active", "toActive"), ("to_reactive", "toReactive")):
             np.testing.assert_allclose(pw[ours], g[theirs], rtol=1.5e-8, atol=1e-10, err_msg=ours)
+
+
+@pytest.mark.parametrize("case,total", [("case14test", 14), ("case30test", 8)])
+def test_reactive_limit_goldens(case, total, ctx):
+    """test/powerFlow/limits.jl:4-43 on the device path: generator outputs (testPower goldens), reactiveLimit!, second
+    Newton-Raphson run on the changed bus types, adjustAngle! -> results.h5:/case/reactiveLimit/newtonRaphson."""
+    g = golden(case)
+    ps = product_system(case)
+    a = jgb200.newton_raphson(ps, ctx)
+    assert jgb200.power_flow(a)
+    pg, qg = jgb200.generator_power(a)
+    np.testing.assert_allclose(pg, g["newtonRaphson"]["generatorActive"], rtol=0, atol=1e-9)
+    np.testing.assert_allclose(qg, g["newtonRaphson"]["generatorReactive"], rtol=0, atol=1e-9)
+    first, slack0 = a.method.iteration, a.slack
+    violate = jgb200.reactive_limit(a)
+    os_ = oracle_system(case)
+    o = onr.newton_raphson(os_)
+    assert onr.power_flow(o)
+    assert np.array_equal(violate, onr.reactive_limit(o))
+    assert np.array_equal(ps.bus_type, os_.bus_type) and ps.slack == os_.slack
+    b = jgb200.newton_raphson(ps, ctx)
+    assert jgb200.power_flow(b)
+    jgb200.adjust_angle(b, slack0)
+    assert b.method.iteration + first == total
+    np.testing.assert_allclose(b.voltage.magnitude, g["reactiveLimit"]["voltageMagnitude"], rtol=0, atol=VOLT_ATOL)
+    np.testing.assert_allclose(b.voltage.angle, g["reactiveLimit"]["voltageAngle"], rtol=0, atol=VOLT_ATOL)

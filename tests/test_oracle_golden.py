@@ -177,3 +177,25 @@ def test_bad_data_largest_normalized_residual_known_answers():
     assert detect and abs(rn - 78.3) < 0.1 and idx == se.range[3] + 3
     assert wls.state_estimation(se)
     assert np.abs(se.vm - a.vm).max() < 1e-10 and np.abs(se.va - a.va).max() < 1e-10
+
+
+@pytest.mark.parametrize("case,total", [("case14test", 14), ("case30test", 8)])
+def test_reactive_limit_goldens(case, total):
+    """test/powerFlow/limits.jl:4-43: NR, reactiveLimit!, NR again, adjustAngle! -> results.h5:/case/reactiveLimit;
+    the generator outputs of the first run are the goldens' generatorActive / generatorReactive."""
+    g = golden(case)
+    s = oracle_system(case)
+    a = nr.newton_raphson(s)
+    assert nr.power_flow(a)
+    pw = post.powers(s, a.mdl, a.vm, a.va)
+    pg, qg = post.generator_powers(s, pw["injection_active"], pw["injection_reactive"], a.slack)
+    np.testing.assert_allclose(pg, g["newtonRaphson"]["generatorActive"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(qg, g["newtonRaphson"]["generatorReactive"], rtol=0, atol=1e-10)
+    first, slack0 = a.iteration, a.slack
+    assert np.any(nr.reactive_limit(a) != 0)
+    b = nr.newton_raphson(s)
+    assert nr.power_flow(b)
+    nr.adjust_angle(b, slack0)
+    assert b.iteration + first == total == int(g["reactiveLimit"]["iteration"][0])
+    np.testing.assert_allclose(b.vm, g["reactiveLimit"]["voltageMagnitude"], rtol=0, atol=1e-10)
+    np.testing.assert_allclose(b.va, g["reactiveLimit"]["voltageAngle"], rtol=0, atol=1e-10)
