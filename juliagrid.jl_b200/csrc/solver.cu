@@ -14,6 +14,10 @@ namespace jgb {
 
 namespace {
 
+// Element offsets: all operands are non-negative 32-bit values, so index products are formed with one widening
+// multiply (mul.wide.u32) or stay in 32 bits, instead of sign-extended 64-bit multiply sequences.
+__device__ __forceinline__ size_t wide(int a, int b) { return (size_t)(unsigned)a * (unsigned)b; }
+
 __device__ __forceinline__ long long urow_off(int p, int nf) {
     return (long long)p * (nf + 1) - (long long)p * (p - 1) / 2;
 }
@@ -51,8 +55,8 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __rest
         const double* __restrict__ av = aval + s;
         const int a1 = sy.f_asmptr[f + 1];
         for (int a = sy.f_asmptr[f] + e0; a < a1; a += TE)
-            Fl[sy.asm_dst[a] * TS] = av[(long long)sy.asm_src[a] * S];
-        for (int p = e0; p < k; p += TE) Fl[(p + nf * nf) * TS] = rhs[(long long)rows[p] * S + s];
+            Fl[sy.asm_dst[a] * TS] = av[wide(sy.asm_src[a], S)];
+        for (int p = e0; p < k; p += TE) Fl[(p + nf * nf) * TS] = rhs[wide(rows[p], S) + s];
     }
     __syncthreads();
     // extend-add of all children as a gather in rounds (child order per destination, so sums are deterministic)
@@ -67,7 +71,7 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __rest
 #pragma unroll 4
                 for (int t = sy.ea_roundptr[r] + e0; t < t1; t += TE) {
                     const int2 pr = sy.ea_pair[t];
-                    Fl[pr.x * TS] += up[(long long)pr.y * W];
+                    Fl[pr.x * TS] += up[(unsigned)(pr.y * W)];
                 }
             }
             __syncthreads();
@@ -207,14 +211,14 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __rest
         double* Urow = Uf + urow_off(p, nf) * S;
         for (int j = p + er; j <= nf; j += TR) {
             const double v = Fl[(p + j * nf) * TS];
-            Urow[(long long)(j - p) * S] = (j == p) ? 1.0 / v : v;
+            Urow[wide(j - p, S)] = (j == p) ? 1.0 / v : v;
         }
     }
     double* __restrict__ Cf = up + sy.f_updoff[f] * W;
     for (int j = ec; j <= u; j += TC) {
         const double* colj = Fl + ((k + j) * nf + k) * TS;
-        double* Cj = Cf + (long long)j * u * W;
-        for (int i = er; i < u; i += TR) Cj[(long long)i * W] = colj[i * TS];
+        double* Cj = Cf + (unsigned)(j * u * W);
+        for (int i = er; i < u; i += TR) Cj[(unsigned)(i * W)] = colj[i * TS];
     }
 }
 
@@ -257,9 +261,9 @@ mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __
         for (int a = sy.f_asmptr[f] + e0; a < a1; a += TE) {
             const int dst = sy.asm_dst[a];
             const int c = dst / nf, r = dst - c * nf;
-            if (r >= c) Fl[(sym_col(c, nf) + r - c) * TS] = av[(long long)sy.asm_src[a] * S];
+            if (r >= c) Fl[(sym_col(c, nf) + r - c) * TS] = av[wide(sy.asm_src[a], S)];
         }
-        for (int p = e0; p < k; p += TE) Rl[p * TS] = rhs[(long long)rows[p] * S + s];
+        for (int p = e0; p < k; p += TE) Rl[p * TS] = rhs[wide(rows[p], S) + s];
     }
     __syncthreads();
     const int W = S < 32 ? S : 32;
@@ -273,8 +277,8 @@ mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __
                 for (int t = sy.ea_roundptr[rd] + e0; t < t1; t += TE) {
                     const int2 pr = sy.ea_pair[t];
                     const int c = pr.x / nf, r = pr.x - c * nf;
-                    if (c == nf) Rl[r * TS] += up[(long long)pr.y * W];
-                    else if (r >= c) Fl[(sym_col(c, nf) + r - c) * TS] += up[(long long)pr.y * W];
+                    if (c == nf) Rl[r * TS] += up[(unsigned)(pr.y * W)];
+                    else if (r >= c) Fl[(sym_col(c, nf) + r - c) * TS] += up[(unsigned)(pr.y * W)];
                 }
             }
             __syncthreads();
@@ -344,12 +348,12 @@ mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __
         const double* colp = Fl + (sym_col(p, nf) - p) * TS;
         for (int j = p + er; j <= nf; j += TR) {
             const double v = (j < nf) ? colp[j * TS] : Rl[p * TS];
-            Urow[(long long)(j - p) * S] = (j == p) ? 1.0 / v : v;
+            Urow[wide(j - p, S)] = (j == p) ? 1.0 / v : v;
         }
     }
     double* __restrict__ Cf = up + sy.f_updoff[f] * W;
     for (int j = ec; j <= u; j += TC) {
-        double* Cj = Cf + (long long)j * u * W;
+        double* Cj = Cf + (unsigned)(j * u * W);
         for (int i = er; i < u; i += TR) {
             double v;
             if (j == u) v = Rl[(k + i) * TS];
@@ -357,7 +361,7 @@ mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __
                 const int r = i >= j ? i : j, c = i >= j ? j : i;
                 v = Fl[(sym_col(k + c, nf) + r - c) * TS];
             }
-            Cj[(long long)i * W] = v;
+            Cj[(unsigned)(i * W)] = v;
         }
     }
 }
@@ -450,7 +454,7 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
         pval[q] = 0.0;
         if (a < a1) {
             pdst[q] = sy.asm_dst[a];
-            pval[q] = av[(long long)sy.asm_src[a] * S];
+            pval[q] = av[wide(sy.asm_src[a], S)];
         }
     }
     constexpr int NPRE_R = 2;
@@ -458,7 +462,7 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
 #pragma unroll
     for (int q = 0; q < NPRE_R; ++q) {
         const int p = e0 + q * TE;
-        prhs[q] = (p < k) ? rhs[(long long)rows[p] * S + s] : 0.0;
+        prhs[q] = (p < k) ? rhs[wide(rows[p], S) + s] : 0.0;
     }
     for (int pos = e0; pos < fsz; pos += TE) Fl[pos * 32] = 0.0;
     __syncthreads();
@@ -466,13 +470,13 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
 #pragma unroll
         for (int q = 0; q < NPRE; ++q)
             if (pdst[q] >= 0) Fl[pdst[q] * 32] = pval[q];
-        for (int a = a0 + e0 + NPRE * TE; a < a1; a += TE) Fl[sy.asm_dst[a] * 32] = av[(long long)sy.asm_src[a] * S];
+        for (int a = a0 + e0 + NPRE * TE; a < a1; a += TE) Fl[sy.asm_dst[a] * 32] = av[wide(sy.asm_src[a], S)];
 #pragma unroll
         for (int q = 0; q < NPRE_R; ++q) {
             const int p = e0 + q * TE;
             if (p < k) Fl[(p + nf * nf) * 32] = prhs[q];
         }
-        for (int p = e0 + NPRE_R * TE; p < k; p += TE) Fl[(p + nf * nf) * 32] = rhs[(long long)rows[p] * S + s];
+        for (int p = e0 + NPRE_R * TE; p < k; p += TE) Fl[(p + nf * nf) * 32] = rhs[wide(rows[p], S) + s];
     }
     uint32_t parity = 0;
     for (int ci = c0; ci < c1;) {
@@ -559,7 +563,7 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
             const int c = e0 + q * TE;
             const double upc = col[q][p];               // U[p, c]
             const bool in = c >= p && c <= nf;
-            if (act && in) Urow[(long long)(c - p) * S] = (c == p) ? inv : upc;
+            if (act && in) Urow[wide(c - p, S)] = (c == p) ? inv : upc;
             m[q] = (in && c > p) ? inv * upc : 0.0;
         }
 #pragma unroll
@@ -576,7 +580,7 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
     for (int q = 0; q < NC; ++q) {
         const int c = e0 + q * TE;
         if (c >= k && c <= nf) {
-            double* Cj = Cf + (long long)(c - k) * u * 32;
+            double* Cj = Cf + (unsigned)((c - k) * u * 32);
 #pragma unroll
             for (int i = 0; i < MAXNF; ++i)
                 if (i >= k && i < nf) Cj[(i - k) * 32] = col[q][i];
@@ -704,8 +708,8 @@ mf_backsolve_tile_kernel(DevSym sy, const int* __restrict__ fronts, const double
     double* xs = sh + sl;                 // xs[j * TS]
     double* Us = sh + nf * TS + sl;       // Us[e * TS], packed rows
     const double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
-    for (int q = e; q < usz; q += TE) Us[q * TS] = Uf[(long long)q * S];
-    for (int j = k + e; j < nf; j += TE) xs[j * TS] = x[(long long)rows[j] * S + s];
+    for (int q = e; q < usz; q += TE) Us[q * TS] = Uf[wide(q, S)];
+    for (int j = k + e; j < nf; j += TE) xs[j * TS] = x[wide(rows[j], S) + s];
     __syncthreads();
     for (int p = e; p < k; p += TE) {
         const double* Urow = Us + (int)urow_off(p, nf) * TS;
@@ -722,7 +726,7 @@ mf_backsolve_tile_kernel(DevSym sy, const int* __restrict__ fronts, const double
     }
     __syncthreads();
     if (act)
-        for (int p = e; p < k; p += TE) x[(long long)rows[p] * S + s] = xs[p * TS];
+        for (int p = e; p < k; p += TE) x[wide(rows[p], S) + s] = xs[p * TS];
 }
 
 void launch_backsolve_tile(int ts, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const int* fronts,
