@@ -175,6 +175,28 @@ int32_t jgb_lin_solve_projected(jgb_ctx* ctx, int64_t R, const double* z, double
 int32_t jgb_lin_solve_dev(jgb_ctx* ctx, int64_t R, const double* in_dev, double* x_dev, int32_t projected);
 int32_t jgb_lin_dims(jgb_ctx* ctx, int64_t* n, int64_t* m, int64_t* nnz_factor, int64_t* fronts);
 
+/* ---- fast Newton-Raphson BX / XB ----------------------------------------------------------------
+ * == AcPowerFlow{FastNewtonRaphson}: mismatch! (src/powerFlow/acPowerFlow.jl:686-727), solve! (:913-983), powerFlow!
+ * (:1389-1433). The constant Jacobians B' (active, (n-1) x (n-1)) and B'' (reactive, npq x npq) are the reference's own
+ * (`fastNewtonRaphsonBX / XB`, :215-339), passed as SparseMatrixCSC; they are factored once on the device (B' may have
+ * unsymmetric values when phase shifters are present). y_t = nodalMatrixTranspose.nzval on the Ybus pattern. */
+int32_t jgb_fnr_setup(jgb_ctx* ctx, int64_t n, const int64_t* y_colptr, const int64_t* y_rowval,
+                      const double* yT_nzval_re_im, const int8_t* bus_type, int64_t slack,
+                      const int64_t* bp_colptr, const int64_t* bp_rowval, const double* bp_nzval,
+                      const int64_t* bq_colptr, const int64_t* bq_rowval, const double* bq_nzval);
+int32_t jgb_fnr_set_injection(jgb_ctx* ctx, const double* p_supply, const double* q_supply, const double* p_demand,
+                              const double* q_demand);
+int32_t jgb_fnr_set_state(jgb_ctx* ctx, const double* vm, const double* va);
+int32_t jgb_fnr_get_state(jgb_ctx* ctx, double* vm, double* va);
+int32_t jgb_fnr_mismatch(jgb_ctx* ctx, double* stop_p, double* stop_q);           /* == mismatch! */
+int32_t jgb_fnr_solve(jgb_ctx* ctx);                                              /* == solve!    */
+int32_t jgb_fnr_run(jgb_ctx* ctx, int64_t max_iter, double tol, int64_t* iterations, double* stop_p, double* stop_q);
+/* R injection scenarios on one topology (the user loop updateBus!(active / reactive) + powerFlow!): p_inj, q_inj [R][n]
+ * = supply - demand per bus; every scenario starts from the state of jgb_fnr_set_state; outputs [R][n];
+ * status 0 converged, 1 iteration cap, -3 diverged. Returns 1 if any scenario did not converge. */
+int32_t jgb_fnr_batch(jgb_ctx* ctx, int64_t R, const double* p_inj, const double* q_inj, int64_t max_iter, double tol,
+                      double* vm_out, double* va_out, int32_t* iterations, int8_t* status, int64_t* total_iterations);
+
 /* ---- statistics for roofline reports ------------------------------------------------------------------------ */
 /* key: "nr.nnz_lu", "nr.fronts", "nr.levels", "nr.flops", "nr.max_front", "nr.launches_per_iteration",
  *      "nr.assemble_bytes" (per scenario-iteration), "nr.solve_bytes", "wls.*" likewise; kernel launch counter

@@ -20,4 +20,7 @@ from .dc_state_estimation import (DcStateEstimation, LinearWls, dc_wls_tables, d
                                   solve_dc_se, dc_se_batch)
 from .pmu_state_estimation import (PmuStateEstimation, pmu_wls_tables, pmu_state_estimation, solve_pmu_se,  # noqa: F401
                                    pmu_se_batch)
+from .fast_newton_raphson import (AcPowerFlowFast, fast_jacobians, fast_newton_raphson_bx,  # noqa: F401
+                                  fast_newton_raphson_xb, mismatch_fnr, solve_fnr, power_flow_fnr, fnr_batch,
+                                  fastNewtonRaphsonBX, fastNewtonRaphsonXB)
 from . import dist  # noqa: F401

@@ -104,6 +104,16 @@ LIN_PROTOTYPES = {
     "jgb_lin_solve_projected": (C.c_int32, [C.c_void_p, C.c_int64, c_f64p, c_f64p]),
     "jgb_lin_solve_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_int32]),
     "jgb_lin_dims": (C.c_int32, [C.c_void_p, c_i64p, c_i64p, c_i64p, c_i64p]),
+    "jgb_fnr_setup": (C.c_int32, [C.c_void_p, C.c_int64, c_i64p, c_i64p, c_f64p, c_i8p, C.c_int64, c_i64p, c_i64p, c_f64p,
+                                  c_i64p, c_i64p, c_f64p]),
+    "jgb_fnr_set_injection": (C.c_int32, [C.c_void_p, c_f64p, c_f64p, c_f64p, c_f64p]),
+    "jgb_fnr_set_state": (C.c_int32, [C.c_void_p, c_f64p, c_f64p]),
+    "jgb_fnr_get_state": (C.c_int32, [C.c_void_p, c_f64p, c_f64p]),
+    "jgb_fnr_mismatch": (C.c_int32, [C.c_void_p, c_f64p, c_f64p]),
+    "jgb_fnr_solve": (C.c_int32, [C.c_void_p]),
+    "jgb_fnr_run": (C.c_int32, [C.c_void_p, C.c_int64, C.c_double, c_i64p, c_f64p, c_f64p]),
+    "jgb_fnr_batch": (C.c_int32, [C.c_void_p, C.c_int64, c_f64p, c_f64p, C.c_int64, C.c_double, c_f64p, c_f64p, c_i32p,
+                                  c_i8p, c_i64p]),
 }
 
 

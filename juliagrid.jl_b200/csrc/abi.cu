@@ -6,6 +6,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "fnr.cuh"
 #include "lin.cuh"
 #include "nr.cuh"
 #include "symbolic.hpp"
@@ -20,6 +21,7 @@ struct jgb_ctx {
     std::string err;
     std::unique_ptr<jgb::NrContext> nr;
     std::unique_ptr<jgb::LinContext> lin;
+    std::unique_ptr<jgb::FnrContext> fnr;
 #ifdef JGB_WITH_WLS
     std::unique_ptr<jgb::WlsContext> wls;
 #endif
@@ -396,6 +398,63 @@ int32_t jgb_lin_dims(jgb_ctx* ctx, int64_t* n, int64_t* m, int64_t* nnz_factor, 
         if (nnz_factor) *nnz_factor = l.nnz_factor();
         if (fronts) *fronts = l.nfronts();
         return 0;
+    });
+}
+
+static jgb::FnrContext& fnr_of(jgb_ctx* ctx) {
+    if (!ctx->fnr) throw std::logic_error("jgb_fnr_setup has not been called on this context");
+    return *ctx->fnr;
+}
+
+int32_t jgb_fnr_setup(jgb_ctx* ctx, int64_t n, const int64_t* y_colptr, const int64_t* y_rowval,
+                      const double* yT_nzval_re_im, const int8_t* bus_type, int64_t slack,
+                      const int64_t* bp_colptr, const int64_t* bp_rowval, const double* bp_nzval,
+                      const int64_t* bq_colptr, const int64_t* bq_rowval, const double* bq_nzval) {
+    return guarded(ctx, [&] {
+        auto f = std::make_unique<jgb::FnrContext>(ctx->stream);
+        f->setup(n, y_colptr, y_rowval, yT_nzval_re_im, bus_type, slack, bp_colptr, bp_rowval, bp_nzval, bq_colptr,
+                 bq_rowval, bq_nzval);
+        ctx->fnr = std::move(f);
+        return 0;
+    });
+}
+
+int32_t jgb_fnr_set_injection(jgb_ctx* ctx, const double* ps, const double* qs, const double* pd, const double* qd) {
+    return guarded(ctx, [&] { fnr_of(ctx).set_injection(ps, qs, pd, qd); return 0; });
+}
+
+int32_t jgb_fnr_set_state(jgb_ctx* ctx, const double* vm, const double* va) {
+    return guarded(ctx, [&] { fnr_of(ctx).set_state(vm, va); return 0; });
+}
+
+int32_t jgb_fnr_get_state(jgb_ctx* ctx, double* vm, double* va) {
+    return guarded(ctx, [&] {
+        if (!vm || !va) throw std::invalid_argument("fnr_get_state: null output");
+        fnr_of(ctx).get_state(vm, va);
+        return 0;
+    });
+}
+
+int32_t jgb_fnr_mismatch(jgb_ctx* ctx, double* stop_p, double* stop_q) {
+    return guarded(ctx, [&] { fnr_of(ctx).mismatch(stop_p, stop_q); return 0; });
+}
+
+int32_t jgb_fnr_solve(jgb_ctx* ctx) {
+    return guarded(ctx, [&] { fnr_of(ctx).solve(); return 0; });
+}
+
+int32_t jgb_fnr_run(jgb_ctx* ctx, int64_t max_iter, double tol, int64_t* iterations, double* stop_p, double* stop_q) {
+    return guarded(ctx, [&] {
+        if (max_iter < 0 || !(tol > 0)) throw std::invalid_argument("fnr_run: max_iter >= 0 and tol > 0 required");
+        return fnr_of(ctx).run(max_iter, tol, iterations, stop_p, stop_q);
+    });
+}
+
+int32_t jgb_fnr_batch(jgb_ctx* ctx, int64_t R, const double* p_inj, const double* q_inj, int64_t max_iter, double tol,
+                      double* vm_out, double* va_out, int32_t* iterations, int8_t* status, int64_t* total_iterations) {
+    return guarded(ctx, [&] {
+        if (max_iter < 0 || !(tol > 0)) throw std::invalid_argument("fnr_batch: max_iter >= 0 and tol > 0 required");
+        return fnr_of(ctx).batch(R, p_inj, q_inj, max_iter, tol, vm_out, va_out, iterations, status, total_iterations);
     });
 }
 

@@ -71,7 +71,7 @@ void LinContext::setup(int64_t n_, const int64_t* cp, const int64_t* rv, const d
             if (t > cp[c] - 1 && rv[t] <= rv[t - 1]) throw std::invalid_argument("lin_setup: rows not sorted");
         }
     }
-    // symmetry of pattern and values (the solver reads the lower triangle only)
+    // the pattern must be symmetric (fixed elimination tree, no pivoting)
     auto find = [&](int r, int c) -> int64_t {
         const int64_t* b = rv + cp[c] - 1;
         const int64_t* e = rv + cp[c + 1] - 1;
@@ -81,13 +81,12 @@ void LinContext::setup(int64_t n_, const int64_t* cp, const int64_t* rv, const d
     for (int c = 0; c < nn; ++c)
         for (int64_t t = cp[c] - 1; t < cp[c + 1] - 1; ++t) {
             const int r = (int)rv[t] - 1;
-            if (r <= c) continue;
-            const int64_t u = find(c, r);
-            if (u < 0) throw std::invalid_argument("lin_setup: pattern is not symmetric");
-            const double a = av[t], b = av[u];
-            if (std::fabs(a - b) > 1e-10 * std::max(std::fabs(a), std::fabs(b)))
-                throw std::invalid_argument("lin_setup: values are not symmetric");
+            if (r != c && find(c, r) < 0) throw std::invalid_argument("lin_setup: pattern is not symmetric");
         }
+    // transpose partner of every stored entry (values may be unsymmetric: fast Newton-Raphson B' with phase shifters)
+    tpos.assign(nnz_in, -1);
+    for (int c = 0; c < nn; ++c)
+        for (int64_t t = cp[c] - 1; t < cp[c + 1] - 1; ++t) tpos[t] = find(c, (int)rv[t] - 1);
     // analysed pattern: the skip row/column reduced to a unit diagonal
     std::vector<int> colptr(nn + 1, 0), rowidx;
     slot.assign(nnz_in, -1);
@@ -118,9 +117,14 @@ void LinContext::setup(int64_t n_, const int64_t* cp, const int64_t* rv, const d
         }
     }
     colptr[nn] = (int)rowidx.size();
+    vals_t = vals;
+    for (size_t t = 0; t < nnz_in; ++t)
+        if (slot[t] >= 0) vals_t[slot[t]] = av[tpos[t]];
     Symbolic sym;
     analyse(nn, colptr.data(), rowidx.data(), nullptr, nullptr, latency_options(), sym);
-    solver.setup(sym, stream, true);
+    symmetric = values_symmetric(av);
+    solver.setup(sym, stream, symmetric);
+    if (!symmetric) solver_t.setup(sym, stream, false);
     std::vector<double> zero(nn, 0.0);
     d_zero.upload(zero, stream);
     d_x0.alloc(nn);
@@ -131,11 +135,24 @@ void LinContext::setup(int64_t n_, const int64_t* cp, const int64_t* rv, const d
     factor_now();
 }
 
+bool LinContext::values_symmetric(const double* av) const {
+    for (size_t t = 0; t < nnz_in; ++t) {
+        const double a = av[t], b = av[tpos[t]];
+        if (std::fabs(a - b) > 1e-12 * std::max(std::fabs(a), std::fabs(b))) return false;
+    }
+    return true;
+}
+
 void LinContext::refactor(const double* av) {
     if (n == 0) throw std::logic_error("jgb_lin_setup has not been called on this context");
     if (!av) throw std::invalid_argument("lin_refactor: null values");
+    if (symmetric && !values_symmetric(av))
+        throw std::invalid_argument("lin_refactor: the matrix was set up as symmetric; the new values are not");
     for (size_t t = 0; t < nnz_in; ++t)
-        if (slot[t] >= 0) vals[slot[t]] = av[t];
+        if (slot[t] >= 0) {
+            vals[slot[t]] = av[t];
+            if (!symmetric) vals_t[slot[t]] = av[tpos[t]];
+        }
     factor_now();
 }
 
@@ -147,7 +164,16 @@ void LinContext::factor_now() {
     JGB_CUDA(cudaMemcpyAsync(h_status.p, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
     JGB_CUDA(cudaStreamSynchronize(stream));
     if (h_status.p[0] != 0) throw std::domain_error("lin: zero or non-finite pivot (singular matrix)");
+    if (!symmetric) {          // the transposed matrix on the same elimination tree supplies L
+        d_aval_t.upload(vals_t, stream);
+        solver_t.factor_solve(d_aval_t.p, d_zero.p, d_x0.p, 1, nullptr, d_status.p, stream);
+        JGB_CUDA(cudaMemcpyAsync(h_status.p, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        JGB_CUDA(cudaStreamSynchronize(stream));
+        if (h_status.p[0] != 0) throw std::domain_error("lin: zero or non-finite pivot (singular matrix)");
+    }
 }
+
+void LinContext::solve_block(double* B, int Rp) { solver.solve_multi(B, Rp, stream, symmetric ? nullptr : &solver_t); }
 
 void LinContext::set_projection(int64_t m_, const int64_t* cp, const int64_t* rv, const double* pv) {
     if (n == 0) throw std::logic_error("jgb_lin_setup has not been called on this context");
@@ -197,7 +223,7 @@ void LinContext::solve(int64_t R, const double* in, bool dev_in, double* out, bo
     } else {
         lin_transpose_in_kernel<<<dim3(ceil_div(nn, 32), Rp / 32), tb, 0, stream>>>(din, d_B.p, nn, Rp, (int)R);
     }
-    solver.solve_multi(d_B.p, Rp, stream);
+    solve_block(d_B.p, Rp);
     double* dout = out;
     if (!dev_out) {
         d_out.alloc((size_t)R * nn);

@@ -1161,8 +1161,10 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
     JGB_CUDA(cudaGetLastError());
 }
 
-void MfSolver::solve_multi(double* B, int R, cudaStream_t st) {
-    if (!symmetric) throw std::logic_error("solve_multi needs a symmetric matrix");
+void MfSolver::solve_multi(double* B, int R, cudaStream_t st, const MfSolver* lower) {
+    if (!symmetric && !lower) throw std::logic_error("solve_multi: an unsymmetric matrix needs the factor of its transpose");
+    if (lower && (lower->planned_S != 1 || lower->sym.u_size != sym.u_size))
+        throw std::logic_error("solve_multi: the transpose factor does not match");
     if (planned_S != 1) throw std::logic_error("solve_multi: factor the matrix (S = 1) first");
     if (R <= 0 || R % 32 != 0) throw std::invalid_argument("solve_multi: the block width must be a multiple of 32");
     if (d_coff.n == 0) {
@@ -1186,7 +1188,8 @@ void MfSolver::solve_multi(double* B, int R, cudaStream_t st) {
         const int b = sym.levelptr[l], e = sym.levelptr[l + 1];
         int threads; size_t smem;
         launch_dims(sym.level_fronts.data(), b, e, threads, smem);
-        mf_fwd_multi_kernel<<<dim3(e - b, R / 32), threads, smem, st>>>(dev, d_level_fronts.p + b, d_U.p, B, d_cvec.p,
+        mf_fwd_multi_kernel<<<dim3(e - b, R / 32), threads, smem, st>>>(dev, d_level_fronts.p + b,
+                                                                          lower ? lower->d_U.p : d_U.p, B, d_cvec.p,
                                                                           d_coff.p, R);
     }
     for (int d = 0; d < sym.ndepths; ++d) {

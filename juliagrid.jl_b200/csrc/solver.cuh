@@ -68,7 +68,9 @@ class MfSolver {
     // After a factor_solve with S == 1 of a symmetric matrix: solve A X = B for a block of R right-hand sides with the
     // stored factor (`solution!` per draw in the reference, utility.jl:576-586). B is [n][R] (entry i of column r at
     // B[i * R + r], R a multiple of 32) and is overwritten by X.
-    void solve_multi(double* B, int R, cudaStream_t st);
+    // Unsymmetric values on a symmetric pattern: pass as `lower` a solver (same symbolic) that factored the transposed
+    // matrix — A = L D U' means A' = U D L', so its packed rows are d_p L[j,p], exactly what the forward sweep needs.
+    void solve_multi(double* B, int R, cudaStream_t st, const MfSolver* lower = nullptr);
     // After a factor_solve with S == 1 of a symmetric matrix: the entries of A^-1 on the pattern of L + L' (sparse
     // selected inverse, what the reference takes from `sparseinv` / Takahashi on the CHOLMOD factor,
     // stateEstimation/badData.jl:330-347, 536-640). Returns the device array; front f holds its nf x nf block (column

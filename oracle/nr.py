@@ -328,3 +328,159 @@ def reactive_limit(a: NewtonRaphson) -> np.ndarray:
 def adjust_angle(a: NewtonRaphson, slack: int):
     """adjustAngle!(analysis; slack) (acPowerFlow.jl:1186-1196)."""
     a.va = a.va + (a.sys.va[slack] - a.va[slack])
+
+
+# ----------------------------------------------------------------------------- fast Newton-Raphson (SURVEY 8f rank 4)
+@dataclass
+class FastNewtonRaphson:
+    sys: System
+    mdl: AcModel
+    bus_type: np.ndarray
+    slack: int
+    vm: np.ndarray
+    va: np.ndarray
+    pq: np.ndarray              # 0-based position among PQ buses, -1 otherwise
+    pvpq: np.ndarray            # 0-based position among non-slack buses, -1 for the slack
+    active: sp.csc_matrix       # B'  ((n-1) x (n-1))
+    reactive: sp.csc_matrix     # B'' (npq x npq)
+    mism_p: np.ndarray
+    mism_q: np.ndarray
+    bx: bool
+    iteration: int = 0
+    lu_p: object = None
+    lu_q: object = None
+
+
+def fast_newton_raphson(sys: System, bx: bool, mdl: AcModel | None = None) -> FastNewtonRaphson:
+    """fastNewtonRaphsonBX / XB (acPowerFlow.jl:215-339): the two constant Jacobians on the Ybus pattern
+    (fastNewtonJacobian :341-412), filled branch by branch (fastNewtonJacobian! :414-451, jacobianCoefficient
+    :453-480, Pijθij / Pijθi :482-505) plus the shunt susceptance of PQ buses (:329-335)."""
+    if mdl is None:
+        mdl = ac_model(sys)
+    bus_type, slack, vm, va = initialize(sys)
+    n = sys.n
+    pq = np.full(n, -1, dtype=np.int64)
+    pvpq = np.full(n, -1, dtype=np.int64)
+    npq = nps = 0
+    for i in range(n):
+        if bus_type[i] == 1:
+            pq[i] = npq; npq += 1
+        if bus_type[i] != 3:
+            pvpq[i] = nps; nps += 1
+    # patterns: for every non-slack column bus the Ybus rows that are non-slack (P) / PQ with a PQ column (Q)
+    rp, cp, rq, cq = [], [], [], []
+    for i in range(n):
+        if i == slack:
+            continue
+        for ptr in range(mdl.colptr[i], mdl.colptr[i + 1]):
+            row = int(mdl.rowval[ptr])
+            if bus_type[row] != 3:
+                rp.append(pvpq[row]); cp.append(pvpq[i])
+            if bus_type[i] == 1 and bus_type[row] == 1:
+                rq.append(pq[row]); cq.append(pq[i])
+    P = sp.lil_matrix((n - 1, n - 1))
+    Q = sp.lil_matrix((npq, npq))
+    for k in range(sys.nbr):
+        if sys.status[k] != 1:
+            continue
+        i, j = int(sys.frm[k]), int(sys.to[k])
+        bsi = 0.5 * sys.b[k]
+        tinv = 1 / sys.tap[k]
+        s, c = np.sin(sys.shift[k]), np.cos(sys.shift[k])
+        if bx:
+            bmk = -1 / sys.x[k]
+            A, B = mdl.admittance[k].real, mdl.admittance[k].imag
+        else:
+            bmk = mdl.admittance[k].imag
+            A, B = 0.0, -1 / sys.x[k]
+        den = c * c + s * s
+        pij, pji = (-A * s - B * c) / den, (A * s - B * c) / den
+        qa, qb, qc = -bmk * tinv, (bmk + bsi) * tinv * tinv, bmk + bsi
+        m_, n_ = pvpq[i], pvpq[j]
+        if i != slack and j != slack:
+            P[m_, n_] += pij
+            P[n_, m_] += pji
+        if i != slack:
+            P[m_, m_] += B / den
+        if j != slack:
+            P[n_, n_] += B
+        ri, rj = pq[i], pq[j]
+        if ri >= 0 and rj >= 0:
+            Q[ri, rj] += qa
+            Q[rj, ri] += qa
+        if bus_type[i] == 1:
+            Q[ri, ri] += qb
+        if bus_type[j] == 1:
+            Q[rj, rj] += qc
+    for i in range(n):
+        if bus_type[i] == 1 and sys.bs[i] != 0:
+            Q[pq[i], pq[i]] += sys.bs[i]
+    # keep the structural pattern of the reference (explicit zeros where branches are out of service)
+    Pp = sp.csc_matrix((np.zeros(len(rp)), (rp, cp)), shape=(n - 1, n - 1))
+    Qp = sp.csc_matrix((np.zeros(len(rq)), (rq, cq)), shape=(npq, npq))
+    return FastNewtonRaphson(sys, mdl, bus_type, slack, vm, va, pq, pvpq, (P.tocsc() + Pp).tocsc(), (Q.tocsc() + Qp).tocsc(),
+                             np.zeros(n - 1), np.zeros(npq), bx)
+
+
+def _fnr_sums(a, i):
+    sys, mdl, V, T = a.sys, a.mdl, a.vm, a.va
+    cur_p = cur_q = 0.0
+    for ptr in range(mdl.colptr[i], mdl.colptr[i + 1]):
+        j = int(mdl.rowval[ptr])
+        y = mdl.nzval_t[ptr]
+        th = T[i] - T[j]
+        sn, cs = sin(th), cos(th)
+        cur_p += V[j] * (y.real * cs + y.imag * sn)
+        cur_q += V[j] * (y.real * sn - y.imag * cs)
+    return cur_p, cur_q
+
+
+def fnr_mismatch(a: FastNewtonRaphson):
+    """mismatch! for the fast method (acPowerFlow.jl:686-727): power mismatches divided by the voltage magnitude."""
+    sys = a.sys
+    stop_p = stop_q = 0.0
+    for i in range(sys.n):
+        if i == a.slack:
+            continue
+        cur_p, cur_q = _fnr_sums(a, i)
+        vinv = 1 / a.vm[i]
+        a.mism_p[a.pvpq[i]] = cur_p - (sys.supply_p[i] - sys.pd[i]) * vinv
+        stop_p = max(stop_p, abs(a.mism_p[a.pvpq[i]]))
+        if a.bus_type[i] == 1:
+            a.mism_q[a.pq[i]] = cur_q - (sys.supply_q[i] - sys.qd[i]) * vinv
+            stop_q = max(stop_q, abs(a.mism_q[a.pq[i]]))
+    return stop_p, stop_q
+
+
+def fnr_solve(a: FastNewtonRaphson):
+    """solve! for the fast method (acPowerFlow.jl:913-983): angle step, reactive mismatch at the new angles, then the
+    magnitude step; both matrices are factored once."""
+    sys = a.sys
+    if a.lu_p is None:
+        a.lu_p = spla.splu(a.active.tocsc())
+        a.lu_q = spla.splu(a.reactive.tocsc())
+    dth = a.lu_p.solve(a.mism_p)
+    for i in range(sys.n):
+        if i != a.slack:
+            a.va[i] += dth[a.pvpq[i]]
+    for i in range(sys.n):
+        if a.bus_type[i] == 1:
+            _, cur_q = _fnr_sums(a, i)
+            a.mism_q[a.pq[i]] = cur_q - (sys.supply_q[i] - sys.qd[i]) / a.vm[i]
+    dv = a.lu_q.solve(a.mism_q)
+    for i in range(sys.n):
+        if a.bus_type[i] == 1:
+            a.vm[i] += dv[a.pq[i]]
+    a.iteration += 1
+
+
+def fnr_power_flow(a: FastNewtonRaphson, iteration: int = 20, tolerance: float = 1e-8) -> bool:
+    a.iteration = 0
+    for _ in range(iteration + 1):
+        sp_, sq_ = fnr_mismatch(a)
+        if sp_ < tolerance and sq_ < tolerance:
+            return True
+        if a.iteration == iteration:
+            break
+        fnr_solve(a)
+    return False

@@ -53,6 +53,9 @@ def main(ref="/root/reference"):
         rl = f"/{case}/reactiveLimit/newtonRaphson"
         out["reactiveLimit"] = {k: np.asarray(res[rl + "/" + k]).reshape(-1).tolist() for k in res.keys(rl)}
         out["source"] += f" + {rl}"
+        for name in ("fastNewtonRaphsonBX", "fastNewtonRaphsonXB"):
+            out[name] = {k: np.asarray(res[f"/{case}/{name}/{k}"]).reshape(-1).tolist() for k in res.keys(f"/{case}/{name}")}
+        out["source"] += f" + /{case}/fastNewtonRaphsonBX|XB"
         with open(os.path.join(HERE, f"{case}.json"), "w") as fh:
             json.dump(out, fh)
         print(case, "iteration", out["newtonRaphson"]["iteration"])

@@ -133,3 +133,20 @@ def test_product_pmu_wls_tables_match_oracle():
         _same_sparse(h, w.coefficient, 1e-12)
         _same_sparse(prec, w.precision, 1e-6 * abs(w.precision).max())
         np.testing.assert_allclose(mean, w.mean, rtol=0, atol=1e-14)
+
+
+def test_product_fast_jacobians_match_oracle():
+    """B' and B'' of fastNewtonRaphsonBX / XB: product (vectorised) vs oracle (branch loop), incl. a phase shifter."""
+    from jgb200.ac_power_flow import _initialize
+    for case in ("case14test", "case30test", "case_ACTIVSg10k"):
+        for bx in (True, False):
+            so, ps = oracle_system(case), product_system(case)
+            if case == "case14test":
+                so.shift[3] = ps.shift[3] = 0.1
+            o = onr.fast_newton_raphson(so, bx)
+            ps.model = jgb200.ac_model(ps)
+            bt, sl, _, _ = _initialize(ps)
+            A, R, pq, pvpq = jgb200.fast_jacobians(ps, ps.model, bt, sl, bx)
+            assert np.array_equal(pq, o.pq) and np.array_equal(pvpq, o.pvpq)
+            _same_sparse(A, o.active, 1e-10)
+            _same_sparse(R, o.reactive, 1e-10)

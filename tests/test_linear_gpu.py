@@ -127,10 +127,19 @@ def test_linear_solver_refactor_and_errors():
     a3 = a.tolil(); a3[17, :] = 0; a3[:, 17] = 0; a3[17, 17] = 1
     np.testing.assert_allclose(x, spla.splu(a3.tocsc()).solve(b[1]), rtol=0, atol=1e-12)
     assert x[17] == b[1][17]
-    # not symmetric -> bad argument; singular -> -3
-    bad = a.copy().tolil(); bad[0, 1] = 5.0; bad[1, 0] = -5.0
+    # unsymmetric values on a symmetric pattern (fast Newton-Raphson B' with phase shifters): A and A' are factored
+    au = a.copy()
+    au.data = au.data * (1.0 + 0.3 * rng.random(len(au.data)))
+    su = jgb200.LinearSolver(au, ctx=s.ctx)
+    np.testing.assert_allclose(su.solve(b), spla.splu(au).solve(b.T).T, rtol=0, atol=1e-12)
+    au2 = au.copy()
+    au2.data = au2.data * (1.0 + 0.1 * rng.random(len(au2.data)))
+    su.refactor(au2)
+    np.testing.assert_allclose(su.solve(b[2]), spla.splu(au2).solve(b[2]), rtol=0, atol=1e-12)
+    # unsymmetric pattern -> bad argument; singular -> -3
+    bad = sp.csc_matrix(np.array([[2.0, 1.0, 0.0], [0.0, 2.0, 1.0], [1.0, 0.0, 2.0]]))
     with pytest.raises(jgb200.JgbError) as e:
-        jgb200.LinearSolver(bad.tocsc(), ctx=s.ctx)
+        jgb200.LinearSolver(bad, ctx=s.ctx)
     assert e.value.rc == -1
     z = sp.csc_matrix(np.array([[1.0, 1.0], [1.0, 1.0]]))
     with pytest.raises(jgb200.JgbError) as e:

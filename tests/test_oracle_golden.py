@@ -199,3 +199,15 @@ def test_reactive_limit_goldens(case, total):
     assert b.iteration + first == total == int(g["reactiveLimit"]["iteration"][0])
     np.testing.assert_allclose(b.vm, g["reactiveLimit"]["voltageMagnitude"], rtol=0, atol=1e-10)
     np.testing.assert_allclose(b.va, g["reactiveLimit"]["voltageAngle"], rtol=0, atol=1e-10)
+
+
+@pytest.mark.parametrize("case,bx,iters", [("case14test", True, 23), ("case14test", False, 23),
+                                           ("case30test", True, 12), ("case30test", False, 9)])
+def test_fast_newton_raphson_goldens(case, bx, iters):
+    """test/powerFlow/analysis.jl:70-150: fastNewtonRaphsonBX / XB iteration counts and voltages from results.h5."""
+    g = golden(case)["fastNewtonRaphsonBX" if bx else "fastNewtonRaphsonXB"]
+    a = nr.fast_newton_raphson(oracle_system(case), bx)
+    assert nr.fnr_power_flow(a, iteration=100)
+    assert a.iteration == iters == int(g["iteration"][0])
+    np.testing.assert_allclose(a.vm, g["voltageMagnitude"], rtol=0, atol=1e-8)
+    np.testing.assert_allclose(a.va, g["voltageAngle"], rtol=0, atol=1e-8)
