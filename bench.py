@@ -192,6 +192,7 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # stdout carries the JSON line only
         dist.init_process_group("nccl", device_id=dev)
     S = args.scenarios
     side = torch.cuda.Stream(device=dev)          # library work and torch CUDA events share this stream
@@ -242,8 +243,18 @@ def run_ours(args):
                                        C.c_void_p(va_d.data_ptr()), C.c_void_p(it_d.data_ptr()),
                                        C.c_void_p(st_d.data_ptr()), C.byref(tot)))
         if world > 1:
-            jgb200.dist.gather_batch_result(vm_d, va_d, it_d, st_d, total_rows=S * world)
+            # the one all-gather of the sweep runs on NCCL's stream while the next batch is solved; at most one is in
+            # flight, and the last one is waited for inside the timed region (finish_device)
+            if pending:
+                pending.pop().wait()
+            pending.append(jgb200.dist.gather_batch_result_async(vm_d, va_d, it_d, st_d))
         return tot.value
+
+    pending = []
+
+    def finish_device():
+        while pending:
+            pending.pop().wait()
 
     def step_host():
         ctx.check(lib.jgb_nr_batch(ctx.handle, S, C.cast(of_h.data_ptr(), C.POINTER(C.c_int64)),
@@ -260,11 +271,13 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, to_device, profile=False):
+    def timed(fn, to_device, profile=False, finish=None):
         """W warm-up steps, then exactly K timed steps between CUDA events; max over ranks."""
         for w in range(args.warmup):
             load(w, to_device)
             fn()
+        if finish:
+            finish()
         if profile:
             torch.cuda.synchronize()
             lib.jgb_profile(ctx.handle, 1)       # phase timers (CUDA events on the same stream) cover the timed region only
@@ -281,6 +294,8 @@ def run_ours(args):
             load(args.warmup + k, to_device)       # device leg: staging the next batch is outside the metric...
             t_host += time.perf_counter() - th
             iters += fn()
+        if finish:
+            finish()                               # outstanding collectives complete inside the timed region
         e1.record()
         barrier()
         wall = time.perf_counter() - w0
@@ -299,7 +314,7 @@ def run_ours(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    ms_dev, iters_dev, launches, _ = timed(step_device, True, profile=True)
+    ms_dev, iters_dev, launches, _ = timed(step_device, True, profile=True, finish=finish_device)
     t_fac, t_bs, t_asm = ctx.stat("nr.time.factor_ms"), ctx.stat("nr.time.backsolve_ms"), ctx.stat("nr.time.assemble_ms")
     n_fac = ctx.stat("nr.time.factor_count")
     lib.jgb_profile(ctx.handle, 0)
@@ -428,6 +443,25 @@ def run_ours(args):
             single["pmu_se_cpu_vs_gpu_max_abs_difference"] = float(np.abs(xs - X[:32]).max())
         except Exception as e:
             single["pmu_se_error"] = str(e)
+        try:
+            # fast Newton-Raphson (XB) on 1024 load scenarios sharing the two device factorisations
+            fa = jgb200.fast_newton_raphson_xb(ps, ctx)
+            Rf = 1024
+            scale = 1.0 + 0.1 * np.random.default_rng(3).standard_normal((Rf, n))
+            sp0, sq0, _ = ps.supply
+            pin = sp0[None, :] - ps.pd[None, :] * scale
+            qin = sq0[None, :] - ps.qd[None, :] * scale
+            jgb200.fnr_batch(fa, pin[:64], qin[:64], iteration=60)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            _, _, fit, fst = jgb200.fnr_batch(fa, pin, qin, iteration=60)
+            torch.cuda.synchronize()
+            single["fnr_scenarios_iterations_per_s_e2e"] = float(fit.sum()) / (time.perf_counter() - t0)
+            single["fnr_scenarios"] = Rf
+            single["fnr_all_converged"] = bool((fst == 0).all())
+            single["fnr_mean_iterations"] = float(fit.mean())
+        except Exception as e:
+            single["fnr_error"] = str(e)
 
     if rank != 0:
         if world > 1:

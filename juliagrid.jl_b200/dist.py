@@ -58,3 +58,33 @@ def gather_batch_result(vm, va, iterations, status, total_rows=None, group=None)
     n = vm.shape[1]
     meta = allgather_rows(torch.stack([iterations.to(torch.int32), status.to(torch.int32)], dim=1), total_rows, group)
     return state[:, :n], state[:, n:], meta[:, 0], meta[:, 1]
+
+
+class PendingGather:
+    """Handle of an all-gather in flight (equal block sizes on every rank): the collective runs on the backend's own
+    stream, so the next batch can be solved while the converged states of this one travel over NVLink. `wait()` makes
+    the current stream wait for it and returns (vm, va, iterations, status) of all ranks."""
+
+    def __init__(self, works, state, meta, n, keep=()):
+        self._works, self._state, self._meta, self._n, self._keep = works, state, meta, n, keep
+
+    def wait(self):
+        for w in self._works:
+            w.wait()
+        self._works, self._keep = [], ()
+        s, m, n = self._state, self._meta, self._n
+        return s[:, :n], s[:, n:], m[:, 0], m[:, 1]
+
+
+def gather_batch_result_async(vm, va, iterations, status, group=None) -> PendingGather:
+    """gather_batch_result without blocking the current stream; every rank must hold the same number of rows."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    src = torch.cat([vm, va], dim=1)                 # private copy: the caller may overwrite vm / va right away
+    meta_src = torch.stack([iterations.to(torch.int32), status.to(torch.int32)], dim=1)
+    state = torch.empty((world * src.shape[0], src.shape[1]), dtype=src.dtype, device=src.device)
+    meta = torch.empty((world * meta_src.shape[0], 2), dtype=torch.int32, device=src.device)
+    works = [dist.all_gather_into_tensor(state, src, group=group, async_op=True),
+             dist.all_gather_into_tensor(meta, meta_src, group=group, async_op=True)]
+    return PendingGather(works, state, meta, vm.shape[1], keep=(src, meta_src))
