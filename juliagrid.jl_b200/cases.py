@@ -112,6 +112,8 @@ def power_system(path: str) -> PowerSystem:
     if path.endswith(".npz"):
         z = np.load(path)
         return _from_mapping({k: z[k] for k in z.files})
+    if path.endswith(".h5"):
+        return _from_hdf5(path)
     text = open(path).read()
     base = float(re.search(r"mpc\.baseMVA\s*=\s*([^;]+);", text).group(1))
     inv = 1.0 / base
@@ -135,6 +137,39 @@ def power_system(path: str) -> PowerSystem:
         ngen=len(gen), gen_bus=look(gen[:, 0]).astype(np.int64), gen_p=gen[:, 1] * inv, gen_q=gen[:, 2] * inv,
         gen_vm=gen[:, 5].copy(), gen_status=gen[:, 7].astype(np.int8), base_mva=base, labels=labels,
         gen_qmin=gen[:, 4] * inv, gen_qmax=gen[:, 3] * inv)
+
+
+def _from_hdf5(path: str) -> PowerSystem:
+    """JuliaGrid's HDF5 case layout (load.jl:141-289): positional 1-based indices, per-unit / radian values, a scalar
+    dataset stands for a constant vector; the base power attribute is in VA."""
+    from .h5 import H5File
+    f = H5File(path)
+    at = f.attrs("/")
+    n, nbr, ngen = (int(at[k]) for k in ("number of buses", "number of branches", "number of generators"))
+
+    def vec(p, count, dtype=np.float64):
+        v = np.asarray(f[p])
+        if v.ndim == 0 or (v.size == 1 and count != 1):
+            return np.full(count, v.reshape(-1)[0], dtype=dtype)
+        return v.astype(dtype)
+
+    bus_type = vec("/bus/layout/type", n, np.int8)
+    sl = np.flatnonzero(bus_type == 3)
+    return PowerSystem(
+        n=n, bus_type=bus_type, slack=int(sl[-1]) if len(sl) else 0,
+        pd=vec("/bus/demand/active", n), qd=vec("/bus/demand/reactive", n),
+        gs=vec("/bus/shunt/conductance", n), bs=vec("/bus/shunt/susceptance", n),
+        vm=vec("/bus/voltage/magnitude", n), va=vec("/bus/voltage/angle", n),
+        nbr=nbr, frm=vec("/branch/layout/from", nbr, np.int64) - 1, to=vec("/branch/layout/to", nbr, np.int64) - 1,
+        r=vec("/branch/parameter/resistance", nbr), x=vec("/branch/parameter/reactance", nbr),
+        g=vec("/branch/parameter/conductance", nbr), b=vec("/branch/parameter/susceptance", nbr),
+        tap=vec("/branch/parameter/turnsRatio", nbr), shift=vec("/branch/parameter/shiftAngle", nbr),
+        status=vec("/branch/layout/status", nbr, np.int8),
+        ngen=ngen, gen_bus=vec("/generator/layout/bus", ngen, np.int64) - 1,
+        gen_p=vec("/generator/output/active", ngen), gen_q=vec("/generator/output/reactive", ngen),
+        gen_vm=vec("/generator/voltage/magnitude", ngen), gen_status=vec("/generator/layout/status", ngen, np.int8),
+        gen_qmin=vec("/generator/capability/minReactive", ngen), gen_qmax=vec("/generator/capability/maxReactive", ngen),
+        base_mva=float(np.asarray(f["/base/power"]).reshape(-1)[0]) / 1e6, labels=list(range(1, n + 1)))
 
 
 def synthetic_grid(side: int = 100, seed: int = 20261017) -> PowerSystem:

@@ -641,24 +641,27 @@ void set_factor_smem_attr() {
 // For each block the packed U rows are staged in shared memory, the part of every row that multiplies already
 // known x (later pivots and update rows) is removed by one warp per row, and warp 0 finishes the 32 x 32 triangle.
 constexpr int kBsRows = 32;
+// The same kernel serves the batch fronts too large for the tile kernel's shared-memory staging (blockIdx.y = scenario,
+// element stride S): strided reads, but only the few top-of-tree fronts of very large cases (e.g. 271 rows at 70k buses).
 __global__ void __launch_bounds__(128)
 mf_backsolve_single(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ U,
-                    double* __restrict__ x, const unsigned char* __restrict__ active) {
+                    double* __restrict__ x, const unsigned char* __restrict__ active, int S) {
     extern __shared__ double sh[];
-    if (active && !active[0]) return;
+    const int s = blockIdx.y;
+    if (active && !active[s]) return;
     const int f = fronts[blockIdx.x];
     const int nf = sy.f_nf[f], k = sy.f_k[f];
     const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
     double* xs = sh;              // nf entries: x of the front rows (pivots filled in as they are solved)
     double* Us = sh + nf;         // packed rows of the current block
-    const double* __restrict__ Uf = U + sy.f_uoff[f];
+    const double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-    for (int j = k + threadIdx.x; j < nf; j += blockDim.x) xs[j] = x[rows[j]];
+    for (int j = k + threadIdx.x; j < nf; j += blockDim.x) xs[j] = x[wide(rows[j], S) + s];
     for (int p1 = k; p1 > 0; p1 -= kBsRows) {
         const int p0 = max(0, p1 - kBsRows);
         const long long base = urow_off(p0, nf);
         const int cnt = (int)(urow_off(p1, nf) - base);
-        for (int e = threadIdx.x; e < cnt; e += blockDim.x) Us[e] = Uf[base + e];
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) Us[e] = Uf[(base + e) * S];
         __syncthreads();
         // rows p0..p1-1: t_p = y_p - sum_{j >= p1} U[p,j] x_j
         for (int p = p0 + warp; p < p1; p += nwarps) {
@@ -685,7 +688,7 @@ mf_backsolve_single(DevSym sy, const int* __restrict__ fronts, const double* __r
         }
         __syncthreads();
     }
-    for (int p = threadIdx.x; p < k; p += blockDim.x) x[rows[p]] = xs[p];
+    for (int p = threadIdx.x; p < k; p += blockDim.x) x[wide(rows[p], S) + s] = xs[p];
 }
 
 // Backward substitution, batch: one CTA per (front, tile of TS scenarios), TE = blockDim / TS lanes per scenario.
@@ -1153,12 +1156,13 @@ void MfSolver::plan(int S) {
                 sl.max_nf = std::max(sl.max_nf, nf);
                 sl.max_k = std::max(sl.max_k, k);
             }
-            if (S > 1) {
+            if (S > 1 && full <= 200 * 1024) {
                 sl.ts = std::min(brules[c].ts, S);
                 while (sl.ts > 1 && full * sl.ts > 100 * 1024) sl.ts /= 2;
                 smem = full * sl.ts;
-                if (smem > 200 * 1024) throw std::runtime_error("front too large for the batch back-solve");
             } else {
+                // single case, or a batch front whose packed rows do not fit shared memory: blocks of 32 rows
+                sl.blocked = true;
                 sl.ts = 1;
                 if (smem > 100 * 1024) throw std::runtime_error("front too large for the back-solve staging buffer");
             }
@@ -1204,8 +1208,9 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
     }
     if (after_factor) JGB_CUDA(cudaEventRecord(after_factor, st));
     for (const SolveLaunch& sl : splan) {
-        if (S == 1) {
-            mf_backsolve_single<<<sl.count, 128, sl.smem, st>>>(dev, d_depth_fronts.p + sl.begin, d_U.p, x, active);
+        if (sl.blocked) {
+            mf_backsolve_single<<<dim3(sl.count, S), 128, sl.smem, st>>>(dev, d_depth_fronts.p + sl.begin, d_U.p, x,
+                                                                        active, S);
         } else if (sl.max_nf <= backsolve_reg_max() && S % 32 == 0) {
             launch_backsolve_reg(sl.max_nf, sl.count, S, st, dev, d_depth_fronts.p + sl.begin, d_U.p, x, active);
         } else {

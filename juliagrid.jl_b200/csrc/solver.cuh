@@ -52,7 +52,8 @@ struct SolveLaunch {
     int begin, count;      // range in depth_fronts
     int max_nf, max_k;
     int ts;                // batch: scenarios per warp (32 / ts lanes cooperate on one scenario)
-    size_t smem;           // S == 1 path only
+    size_t smem;
+    bool blocked;          // 32-row blocked kernel (single case; batch fronts too large for the tile staging)
 };
 
 class MfSolver {

@@ -26,7 +26,7 @@ def oracle_system(name):
         return oracle.synthetic_grid()
     if name.startswith("synthetic"):
         return oracle.synthetic_grid(side=int(name[len("synthetic"):]))
-    if name == "case_ACTIVSg10k":
+    if name.startswith("case_ACTIVSg"):
         z = np.load(os.path.join(GOLDEN, name + ".npz"))
         return oracle.system_from_arrays({k: z[k] for k in z.files})
     return oracle.system_from_arrays(golden(name)["system"])
@@ -38,7 +38,7 @@ def product_system(name):
         return jgb200.synthetic_grid()
     if name.startswith("synthetic"):
         return jgb200.synthetic_grid(side=int(name[len("synthetic"):]))
-    if name == "case_ACTIVSg10k":
+    if name.startswith("case_ACTIVSg"):
         return jgb200.power_system(os.path.join(GOLDEN, name + ".npz"))
     return jgb200.power_system(os.path.join(GOLDEN, name + ".json"))
 

@@ -67,6 +67,12 @@ def main(ref="/root/reference"):
                         base_mva=s.base_mva, **arrays)
     print("ACTIVSg10k", s.n, s.nbr, s.ngen, os.path.getsize(os.path.join(HERE, "case_ACTIVSg10k.npz")))
 
+    # the largest single-interconnect case the reference ships (70 000 buses): scale test of the single-case path
+    s = load_hdf5(os.path.join(ref, "docs/src/examples/cases/hdf5/case_ACTIVSg70k.h5"))
+    np.savez_compressed(os.path.join(HERE, "case_ACTIVSg70k.npz"), n=s.n, nbr=s.nbr, ngen=s.ngen, slack=s.slack,
+                        base_mva=s.base_mva, **{k: getattr(s, k) for k in SYS_FIELDS})
+    print("ACTIVSg70k", s.n, s.nbr, s.ngen, os.path.getsize(os.path.join(HERE, "case_ACTIVSg70k.npz")))
+
     known = {
         "badData_one_outlier": {
             "source": "test/stateEstimation/badData.jl:5-41",

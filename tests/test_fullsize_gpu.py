@@ -81,3 +81,33 @@ def test_monte_carlo_wls_10k_chi_square(ctx):
     np.testing.assert_allclose(res.vm[11], se.voltage.magnitude, atol=1e-11)
     np.testing.assert_allclose(res.va[11], se.voltage.angle, atol=1e-11)
     assert res.iterations[11] == se.method.iteration
+
+
+def test_70k_bus_case_single_and_outage_batch(ctx):
+    """The largest single-interconnect case the reference ships (case_ACTIVSg70k.h5: 70 000 buses, 88 207 branches,
+    dim J = 129 k): index sets bit-exact, Newton-Raphson from the stored profile equals the oracle (6 iterations,
+    1e-8), and a 64-outage batch satisfies the oracle's equations of the modified grids."""
+    ps, os_ = product_system("case_ACTIVSg70k"), oracle_system("case_ACTIVSg70k")
+    a = jgb200.newton_raphson(ps, ctx)
+    base = oracle.ac_model(os_)
+    o = onr.newton_raphson(os_, base)
+    m, ex = a.method, onr.export_one_based(o)
+    for mine, key in ((m.pq, "pq"), (m.pvpq, "pvpq"), (m.pcount, "pcount"), (m.jacobian_colptr, "j_colptr"),
+                      (m.jacobian_rowval, "j_rowval")):
+        assert np.array_equal(mine, ex[key]), key
+    f = FastNR(o)
+    assert f.power_flow() and jgb200.power_flow(a)
+    assert a.method.iteration == f.iteration == 6
+    assert np.abs(a.voltage.magnitude - f.vm).max() < 1e-8 and np.abs(a.voltage.angle - f.va).max() < 1e-8
+    elig = jgb200.eligible_outages(ps)
+    ks = elig[np.linspace(0, len(elig) - 1, 64).astype(int)]
+    res = jgb200.nr_batch(a, ks)
+    ok = res.status == 0
+    assert ok.sum() >= 60                      # a few heavy corridors of this case have no N-1 solution from this start
+    for pos in np.flatnonzero(ok)[[0, 20, -1]]:
+        mo = apply_outage(os_, base, int(ks[pos]))
+        f.set_y(mo.nzval, mo.nzval_t)
+        f.vm[:] = res.vm[pos]
+        f.va[:] = res.va[pos]
+        dp, dq = f.mismatch()
+        assert dp < 1e-8 and dq < 1e-8
