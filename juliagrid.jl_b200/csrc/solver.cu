@@ -645,7 +645,7 @@ constexpr int kBsRows = 32;
 // element stride S): strided reads, but only the few top-of-tree fronts of very large cases (e.g. 271 rows at 70k buses).
 __global__ void __launch_bounds__(128)
 mf_backsolve_single(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ U,
-                    double* __restrict__ x, const unsigned char* __restrict__ active, int S) {
+                    double* __restrict__ x, const unsigned char* __restrict__ active, int S, int bs_rows) {
     extern __shared__ double sh[];
     const int s = blockIdx.y;
     if (active && !active[s]) return;
@@ -657,8 +657,8 @@ mf_backsolve_single(DevSym sy, const int* __restrict__ fronts, const double* __r
     const double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int j = k + threadIdx.x; j < nf; j += blockDim.x) xs[j] = x[wide(rows[j], S) + s];
-    for (int p1 = k; p1 > 0; p1 -= kBsRows) {
-        const int p0 = max(0, p1 - kBsRows);
+    for (int p1 = k; p1 > 0; p1 -= bs_rows) {       // bs_rows <= 32: one lane of warp 0 per row of the block
+        const int p0 = max(0, p1 - bs_rows);
         const long long base = urow_off(p0, nf);
         const int cnt = (int)(urow_off(p1, nf) - base);
         for (int e = threadIdx.x; e < cnt; e += blockDim.x) Us[e] = Uf[(base + e) * S];
@@ -1008,7 +1008,7 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
 #undef X
     dev.upd_size = sym.upd_size;
     dev.child_desc = d_child_desc.p;
-    JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 
 namespace {
@@ -1164,7 +1164,19 @@ void MfSolver::plan(int S) {
                 // single case, or a batch front whose packed rows do not fit shared memory: blocks of 32 rows
                 sl.blocked = true;
                 sl.ts = 1;
-                if (smem > 100 * 1024) throw std::runtime_error("front too large for the back-solve staging buffer");
+                sl.bs_rows = kBsRows;           // fewer rows per block when 32 packed rows exceed shared memory
+                auto need = [&](int rows_) {
+                    size_t worst = 0;
+                    for (int q = i; q < j; ++q) {
+                        const int f = sym.depth_fronts[q];
+                        const int nf = sym.f_nf[f], kb = std::min(sym.f_k[f], rows_);
+                        worst = std::max(worst, ((size_t)kb * (nf + 1) - (size_t)kb * (kb - 1) / 2 + nf) * sizeof(double));
+                    }
+                    return worst;
+                };
+                while (sl.bs_rows > 1 && need(sl.bs_rows) > 200 * 1024) sl.bs_rows /= 2;
+                smem = need(sl.bs_rows);
+                if (smem > 200 * 1024) throw std::runtime_error("front too large for the back-solve staging buffer");
             }
             sl.smem = smem;
             splan.push_back(sl);
@@ -1210,7 +1222,7 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
     for (const SolveLaunch& sl : splan) {
         if (sl.blocked) {
             mf_backsolve_single<<<dim3(sl.count, S), 128, sl.smem, st>>>(dev, d_depth_fronts.p + sl.begin, d_U.p, x,
-                                                                        active, S);
+                                                                        active, S, sl.bs_rows);
         } else if (sl.max_nf <= backsolve_reg_max() && S % 32 == 0) {
             launch_backsolve_reg(sl.max_nf, sl.count, S, st, dev, d_depth_fronts.p + sl.begin, d_U.p, x, active);
         } else {

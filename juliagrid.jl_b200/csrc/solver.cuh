@@ -53,6 +53,7 @@ struct SolveLaunch {
     int max_nf, max_k;
     int ts;                // batch: scenarios per warp (32 / ts lanes cooperate on one scenario)
     size_t smem;
+    int bs_rows;           // rows per block of the blocked kernel (<= 32)
     bool blocked;          // 32-row blocked kernel (single case; batch fronts too large for the tile staging)
 };
 

@@ -111,3 +111,26 @@ def test_70k_bus_case_single_and_outage_batch(ctx):
         f.va[:] = res.va[pos]
         dp, dq = f.mismatch()
         assert dp < 1e-8 and dq < 1e-8
+
+
+def test_70k_bus_state_estimation_recovers_power_flow(ctx):
+    """Config-3 measurement set on the 70 000-bus case (m = 0.57 M rows, gain fronts beyond the shared-memory LDLt
+    limit): exact measurements of the power-flow state are recovered (test/stateEstimation/analysis.jl recovery
+    property), and the chi-square / residual tests see no bad data."""
+    ps = product_system("case_ACTIVSg70k")
+    a = jgb200.newton_raphson(ps, ctx)
+    assert jgb200.power_flow(a)
+    vm, va = a.voltage.magnitude, a.voltage.angle
+    pw = jgb200.power(ps, vm, va)
+    mon = jgb200.measurement(ps)
+    jgb200.add_voltmeter(mon, vm)
+    jgb200.add_wattmeter(mon, pw)
+    jgb200.add_varmeter(mon, pw)
+    buses = np.sort(np.random.default_rng(7).choice(ps.n, ps.n // 10, replace=False))
+    jgb200.add_pmu(mon, pw, vm, va, buses=buses, polar=False)
+    se = jgb200.gauss_newton(mon, ctx)
+    assert jgb200.state_estimation(se)
+    assert se.method.iteration <= 6
+    assert np.abs(se.voltage.magnitude - vm).max() < 1e-8 and np.abs(se.voltage.angle - va).max() < 1e-8
+    assert not jgb200.chi_test(se).detect
+    assert not jgb200.residual_test(se).detect
