@@ -243,6 +243,42 @@ function JuliaGrid.residualTest!(a::AcStateEstimationB200; threshold::Float64 = 
     return bad
 end
 
+# ---- fast Newton-Raphson BX / XB: JuliaGrid builds the two constant Jacobians, the device factors them once ----------
+mutable struct FastNewtonRaphsonB200
+    ctx::Ctx
+    reference::Any            # the reference's own analysis (bus-type fix-ups, start point, B' and B'')
+    iteration::Int64
+end
+
+function fastNewtonRaphsonB200(system::PowerSystem; bx::Bool = true, device::Integer = 0)
+    ref = bx ? JuliaGrid.fastNewtonRaphsonBX(system) : JuliaGrid.fastNewtonRaphsonXB(system)
+    Y, Yt, bus = system.model.ac.nodalMatrix, system.model.ac.nodalMatrixTranspose, system.bus
+    Bp, Bq = ref.method.active.jacobian, ref.method.reactive.jacobian
+    ctx = Ctx(device)
+    GC.@preserve Y Yt Bp Bq check(ctx, ccall((:jgb_fnr_setup, libjgb), Int32,
+        (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64}, Ptr{Int8}, Int64, Ptr{Int64}, Ptr{Int64}, Ptr{Float64},
+         Ptr{Int64}, Ptr{Int64}, Ptr{Float64}),
+        ctx.handle, bus.number, Y.colptr, Y.rowval, pointer(reinterpret(Float64, Yt.nzval)), bus.layout.type,
+        bus.layout.slack, Bp.colptr, Bp.rowval, Bp.nzval, Bq.colptr, Bq.rowval, Bq.nzval))
+    check(ctx, ccall((:jgb_fnr_set_injection, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+        ctx.handle, bus.supply.active, bus.supply.reactive, bus.demand.active, bus.demand.reactive))
+    check(ctx, ccall((:jgb_fnr_set_state, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+        ctx.handle, ref.voltage.magnitude, ref.voltage.angle))
+    return FastNewtonRaphsonB200(ctx, ref, 0)
+end
+
+"powerFlow! for the fast method on the device; the voltages land in `a.reference.voltage`."
+function powerFlowB200!(a::FastNewtonRaphsonB200; iteration::Int64 = 20, tolerance::Float64 = 1e-8)
+    it, sp, sq = Ref{Int64}(0), Ref{Float64}(0), Ref{Float64}(0)
+    rc = check(a.ctx, ccall((:jgb_fnr_run, libjgb), Int32, (Ptr{Cvoid}, Int64, Float64, Ref{Int64}, Ref{Float64}, Ref{Float64}),
+        a.ctx.handle, iteration, tolerance, it, sp, sq))
+    a.iteration = it[]
+    v = a.reference.voltage
+    check(a.ctx, ccall((:jgb_fnr_get_state, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+        a.ctx.handle, v.magnitude, v.angle))
+    return rc == 0
+end
+
 # ---- linear analyses (DC power flow, DC and PMU state estimation): one device factorisation, many right-hand sides ----
 # The reference's own setup functions build every table (`dcPowerFlow`, `dcStateEstimation`, `pmuStateEstimation`
 # with the default LU tag); only `factorization / solution!` is replaced (src/backend/utility.jl:470-586).
@@ -307,6 +343,6 @@ function linearEstimationB200(se, Z::Matrix{Float64}; slack::Integer = 0, device
     return projectedSolution(F, Z)
 end
 
-export B200, LinearB200, projection!, solution, projectedSolution, dcPowerFlowB200, linearEstimationB200
+export B200, fastNewtonRaphsonB200, powerFlowB200!, LinearB200, projection!, solution, projectedSolution, dcPowerFlowB200, linearEstimationB200
 
 end # module
