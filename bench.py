@@ -376,8 +376,8 @@ def run_ours(args):
             torch.cuda.synchronize()
             single["wls_residual_test_ms"] = (time.perf_counter() - t0) * 1e3
             single["wls_max_normalized_residual"] = rt.maxNormalizedResidual
-            # configs[4]-style Monte-Carlo batch: 256 noise draws of the same measurement set on this GPU
-            Sm = 256
+            # configs[4]: the 1000 Monte-Carlo noise draws of the same measurement set, all on this GPU
+            Sm = 1000
             Z = np.stack([t.mean + np.sqrt(1 / wd) * np.random.default_rng(1000 + q).standard_normal(t.m)
                           for q in range(Sm)])
             jgb200.set_voltage_se(se, ps.vm, ps.va)
