@@ -27,7 +27,7 @@ __device__ __forceinline__ long long urow_off(int p, int nf) {
 // element (r,c) of scenario lane sl at F[(r + c*nf) * TS + sl].  TS and the address space of F are compile-time
 // so that the front is addressed with LDS/STS and shifts (a runtime select would degrade to generic LD/ST).
 template <int TS, bool GLOBAL_F>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TS == 1 ? 512 : 256)
 mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ aval,
                  const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S,
                  int TR, const unsigned char* __restrict__ active, int* __restrict__ status, double* gwork,
@@ -233,7 +233,7 @@ constexpr int kMaxSymFront = 208;
 __device__ __forceinline__ int sym_col(int j, int nf) { return (j * (2 * nf - j + 1)) >> 1; }
 
 template <int TS>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(TS == 1 ? 1024 : 256)
 mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ aval,
                      const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S, int TR,
                      const unsigned char* __restrict__ active, int* __restrict__ status) {
@@ -1041,13 +1041,17 @@ void MfSolver::plan(int S) {
     // single case: one launch per level (launch latency dominates; measured 625 us vs 855 us per factorisation with
     // four size classes on the 10k-bus Jacobian)
     static const std::vector<PlanRule> single_rules = {{kMaxSmemFront, 1, 256}, {kMaxSymFront, 1, 256}};
+    // LDL^T (WLS gain, linear analyses): a front is one CTA on one SM and the big fronts sit alone at the top of the
+    // tree, so wider CTAs pay: measured on the 10k-bus gain matrix 4.21 ms per factorisation with 256 threads, 2.74 ms
+    // with 512 threads up to 64 rows and 1024 above (the LU kernel of the Jacobian, fronts <= 66, is best at 256)
+    static const std::vector<PlanRule> single_rules_sym = {{64, 1, 512}, {kMaxSymFront, 1, 1024}};
     static const std::vector<PlanRule> batch_rules = {{8, 32, 128}, {12, 32, 128}, {16, 32, 256}, {20, 16, 256},
                                                       {24, 8, 256}, {32, 8, 256}, {48, 4, 256}, {64, 2, 256},
                                                       {96, 1, 256}, {kMaxSmemFront, 1, 256},
                                                       {kMaxSymFront, 1, 256}};
     const char* nb = getenv("JGB_NO_BULK");
     const bool bulk_enabled = !(nb && *nb == '1');
-    const std::vector<PlanRule> rules = (S == 1) ? parse_rules("JGB_FPLAN_SINGLE", single_rules)
+    const std::vector<PlanRule> rules = (S == 1) ? parse_rules("JGB_FPLAN_SINGLE", symmetric ? single_rules_sym : single_rules)
                                                  : parse_rules("JGB_FPLAN_BATCH", batch_rules);
     auto cls = [&](int nf) { size_t c = 0; while (c < rules.size() && nf > rules[c].maxnf) ++c; return (int)c; };
     for (int l = 0; l < sym.nlevels; ++l) {
@@ -1093,11 +1097,13 @@ void MfSolver::plan(int S) {
             if (fl.bulk) {
             } else if (fl.global_front) {
                 fl.ts = (S == 1) ? 1 : 4;
-                fl.threads = 256;
+                fl.threads = (S == 1) ? 512 : 256;
             } else {
                 const PlanRule& rl = rules[std::min<size_t>(c, rules.size() - 1)];
                 fl.ts = std::min(rl.ts, S);
                 fl.threads = std::max(rl.threads, fl.ts);
+                // launch bounds: 256 threads for scenario tiles, 512 (LU) / 1024 (LDL^T) for single-scenario CTAs
+                fl.threads = std::min(fl.threads, fl.ts > 1 ? 256 : (fl.sym ? 1024 : 512));
                 while (fl.ts > 1 && per * fl.ts > 200 * 1024) fl.ts /= 2;
             }
             int te = fl.threads / fl.ts;
