@@ -643,7 +643,7 @@ void set_factor_smem_attr() {
 constexpr int kBsRows = 32;
 // The same kernel serves the batch fronts too large for the tile kernel's shared-memory staging (blockIdx.y = scenario,
 // element stride S): strided reads, but only the few top-of-tree fronts of very large cases (e.g. 271 rows at 70k buses).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(512)
 mf_backsolve_single(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ U,
                     double* __restrict__ x, const unsigned char* __restrict__ active, int S, int bs_rows) {
     extern __shared__ double sh[];
@@ -918,6 +918,13 @@ mf_selinv_kernel(DevSym sy, const int* __restrict__ fronts, const int* __restric
         if (threadIdx.x == 0) Zf[p + (long long)p * nf] = s_diag;
         __syncthreads();
     }
+}
+
+int backsolve_single_threads() {
+    // one CTA per front: measured single-case back-solve of the 10k-bus Jacobian 293 / 248 / 239 us with 128 / 256 / 512
+    // threads (gain matrix: 0.83 / 0.62 / 0.53 ms). JGB_BS_THREADS overrides (<= 512; tuning only).
+    static const int v = getenv("JGB_BS_THREADS") ? std::min(512, std::max(32, atoi(getenv("JGB_BS_THREADS")))) : 512;
+    return v;
 }
 
 int backsolve_reg_max() {
@@ -1227,7 +1234,7 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
     if (after_factor) JGB_CUDA(cudaEventRecord(after_factor, st));
     for (const SolveLaunch& sl : splan) {
         if (sl.blocked) {
-            mf_backsolve_single<<<dim3(sl.count, S), 128, sl.smem, st>>>(dev, d_depth_fronts.p + sl.begin, d_U.p, x,
+            mf_backsolve_single<<<dim3(sl.count, S), backsolve_single_threads(), sl.smem, st>>>(dev, d_depth_fronts.p + sl.begin, d_U.p, x,
                                                                         active, S, sl.bs_rows);
         } else if (sl.max_nf <= backsolve_reg_max() && S % 32 == 0) {
             launch_backsolve_reg(sl.max_nf, sl.count, S, st, dev, d_depth_fronts.p + sl.begin, d_U.p, x, active);
