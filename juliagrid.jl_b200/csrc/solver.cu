@@ -1056,10 +1056,16 @@ void MfSolver::plan(int S) {
                                                       {24, 8, 256}, {32, 8, 256}, {48, 4, 256}, {64, 2, 256},
                                                       {96, 1, 256}, {kMaxSmemFront, 1, 256},
                                                       {kMaxSymFront, 1, 256}};
+    // LDL^T batches (WLS Monte-Carlo): the single-scenario classes of the big gain fronts take wider CTAs (factor phase
+    // of 512 draws 33.8 -> 29.5 ms); the LU batch of the Jacobian is best with 256 everywhere (48.3 vs 50.2 ms)
+    static const std::vector<PlanRule> batch_rules_sym = {{8, 32, 128}, {12, 32, 128}, {16, 32, 256}, {20, 16, 256},
+                                                          {24, 8, 256}, {32, 8, 256}, {48, 4, 256}, {64, 2, 256},
+                                                          {96, 1, 256}, {kMaxSmemFront, 1, 512},
+                                                          {kMaxSymFront, 1, 1024}};
     const char* nb = getenv("JGB_NO_BULK");
     const bool bulk_enabled = !(nb && *nb == '1');
     const std::vector<PlanRule> rules = (S == 1) ? parse_rules("JGB_FPLAN_SINGLE", symmetric ? single_rules_sym : single_rules)
-                                                 : parse_rules("JGB_FPLAN_BATCH", batch_rules);
+                                                 : parse_rules("JGB_FPLAN_BATCH", symmetric ? batch_rules_sym : batch_rules);
     auto cls = [&](int nf) { size_t c = 0; while (c < rules.size() && nf > rules[c].maxnf) ++c; return (int)c; };
     for (int l = 0; l < sym.nlevels; ++l) {
         int b = sym.levelptr[l], e = sym.levelptr[l + 1];
