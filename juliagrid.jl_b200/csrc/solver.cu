@@ -872,7 +872,7 @@ mf_bwd_multi_kernel(DevSym sy, const int* __restrict__ fronts, const double* __r
 // at zoff[f]; the entries of A^-1 on the pattern of L + L' are exactly the union of these blocks. One CTA per front,
 // the block lives in global memory (L2) because the largest fronts exceed shared memory; this is a one-off post-step
 // (largest normalised residual, badData.jl:181-285), not part of the iteration loop.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(1024)
 mf_selinv_kernel(DevSym sy, const int* __restrict__ fronts, const int* __restrict__ parent,
                  const double* __restrict__ U, double* __restrict__ Z, const long long* __restrict__ zoff) {
     extern __shared__ double sh[];          // lvec[nf] | zcol[nf]
@@ -918,6 +918,12 @@ mf_selinv_kernel(DevSym sy, const int* __restrict__ fronts, const int* __restric
         if (threadIdx.x == 0) Zf[p + (long long)p * nf] = s_diag;
         __syncthreads();
     }
+}
+
+int selinv_threads(int max_nf) {      // one CTA per front; JGB_SELINV_THREADS overrides (tuning only)
+    static const int v = getenv("JGB_SELINV_THREADS") ? atoi(getenv("JGB_SELINV_THREADS")) : 0;
+    if (v > 0) return std::min(1024, std::max(32, v));
+    return max_nf <= 64 ? 256 : 1024;
 }
 
 int backsolve_single_threads() {
@@ -1308,7 +1314,7 @@ const double* MfSolver::selected_inverse(cudaStream_t st) {
         const int b = sym.depthptr[d], e = sym.depthptr[d + 1];
         int mx = 0;
         for (int q = b; q < e; ++q) mx = std::max(mx, sym.f_nf[sym.depth_fronts[q]]);
-        mf_selinv_kernel<<<e - b, 256, 2 * (size_t)mx * sizeof(double), st>>>(dev, d_depth_fronts.p + b, d_parent.p,
+        mf_selinv_kernel<<<e - b, selinv_threads(mx), 2 * (size_t)mx * sizeof(double), st>>>(dev, d_depth_fronts.p + b, d_parent.p,
                                                                               d_U.p, d_Zinv.p, d_zoff.p);
     }
     JGB_CUDA(cudaGetLastError());
