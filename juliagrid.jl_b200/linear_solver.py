@@ -56,12 +56,15 @@ class LinearSolver:
                                                   ptr(x, C.c_double)))
         return x.reshape(np.shape(b))
 
-    def solve_projected(self, z) -> np.ndarray:
-        """z: [m] or [R][m] measurement vectors; returns x [n] or [R][n]."""
+    def solve_projected(self, z, out=None) -> np.ndarray:
+        """z: [m] or [R][m] measurement vectors; returns x [n] or [R][n]. `out` (optional, [R][n] float64, e.g. a view
+        of pinned memory) receives the result without an extra allocation."""
         z2 = f64(np.atleast_2d(z))
         if z2.shape[1] != self.m:
             raise ValueError("measurement vector must have m entries")
-        x = np.empty((z2.shape[0], self.n))
+        x = np.empty((z2.shape[0], self.n)) if out is None else out
+        if x.shape != (z2.shape[0], self.n) or x.dtype != np.float64 or not x.flags.c_contiguous:
+            raise ValueError("out must be a C-contiguous float64 array of shape [R][n]")
         self.ctx.check(self.ctx.lib.jgb_lin_solve_projected(self.ctx.handle, z2.shape[0], ptr(z2, C.c_double),
                                                             ptr(x, C.c_double)))
         return x[0] if np.ndim(z) == 1 else x
