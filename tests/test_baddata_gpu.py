@@ -119,3 +119,18 @@ def test_projection_10k_sample(ctx):
     assert bad.detect and bad.label == ("wattmeter", 1234)
     assert jgb200.state_estimation(se)
     assert np.abs(se.voltage.magnitude - o.vm).max() < 1e-8 and np.abs(se.voltage.angle - o.va).max() < 1e-8
+
+
+def test_residual_test_needs_a_solved_estimation_and_valid_rows(ctx):
+    fresh = jgb200.Context(0)
+    rn, idx = C.c_double(0), C.c_int64(0)
+    assert fresh.lib.jgb_wls_residual_test(fresh.handle, 3.0, C.byref(rn), C.byref(idx), None) == -1   # no setup
+    so, o, me, mon = _product_case(False)
+    se = jgb200.gauss_newton(mon, fresh)
+    assert fresh.lib.jgb_wls_remove_row(fresh.handle, 0) == -1
+    assert fresh.lib.jgb_wls_remove_row(fresh.handle, se.method.tables.m + 1) == -1
+    assert jgb200.state_estimation(se)
+    bad = jgb200.residual_test(se, threshold=1e6)          # nothing exceeds the threshold: nothing is removed
+    assert not bad.detect and bad.index >= 0 and mon.var["status"][3] == 1
+    assert np.count_nonzero(se.method.type) == se.method.tables.m
+    fresh.close()

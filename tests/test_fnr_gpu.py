@@ -89,3 +89,20 @@ def test_injection_scenarios_share_the_factorisations(ctx):
         assert np.abs(vm[r] - o.vm).max() < VOLT_ATOL and np.abs(va[r] - o.va).max() < VOLT_ATOL
     # the single-case surface still works after a batch
     assert jgb200.power_flow_fnr(a, iteration=100) and a.method.iteration == 9
+
+
+def test_bad_arguments_and_iteration_cap(ctx):
+    import ctypes as C
+    fresh = jgb200.Context(0)
+    v = np.zeros(4)
+    p = v.ctypes.data_as(C.POINTER(C.c_double))
+    assert fresh.lib.jgb_fnr_set_state(fresh.handle, p, p) == -1          # before setup
+    assert fresh.lib.jgb_fnr_run(fresh.handle, 10, 1e-8, None, None, None) == -1
+    a = _make(product_system("case14test"), True, fresh)
+    assert fresh.lib.jgb_fnr_run(fresh.handle, -1, 1e-8, None, None, None) == -1
+    assert fresh.lib.jgb_fnr_run(fresh.handle, 10, 0.0, None, None, None) == -1
+    assert fresh.lib.jgb_fnr_set_state(fresh.handle, None, p) == -1
+    # the iteration cap is a soft status (rc 1), like the reference's powerFlow! without convergence
+    assert not jgb200.power_flow_fnr(a, iteration=3) and a.method.iteration == 3
+    assert jgb200.power_flow_fnr(a, iteration=100)
+    fresh.close()

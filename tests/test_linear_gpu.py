@@ -146,3 +146,40 @@ def test_linear_solver_refactor_and_errors():
         jgb200.LinearSolver(z, ctx=s.ctx)
     assert e.value.rc == -3
     s.ctx.close()
+
+
+def test_lin_edge_cases_and_bad_arguments(ctx):
+    """Ragged block widths (1, 33: not multiples of the 32-wide tile), calls out of order and null pointers."""
+    import ctypes as C
+    lib = ctx.lib
+    rng = np.random.default_rng(9)
+    n = 50
+    a = sp.random(n, n, density=0.08, random_state=3, format="csc")
+    a = (a + a.T + sp.diags(np.full(n, 6.0))).tocsc()
+    fresh = jgb200.Context(0)
+    # solve before setup -> bad argument / logic error, not a crash
+    x = np.empty(n)
+    rc = fresh.lib.jgb_lin_solve(fresh.handle, 1, x.ctypes.data_as(C.POINTER(C.c_double)), x.ctypes.data_as(C.POINTER(C.c_double)))
+    assert rc == -1 and b"jgb_lin_setup" in fresh.lib.jgb_last_error(fresh.handle)
+    s = jgb200.LinearSolver(a, ctx=fresh)
+    lu = spla.splu(a)
+    for R in (1, 33):
+        b = rng.standard_normal((R, n))
+        np.testing.assert_allclose(s.solve(b), lu.solve(b.T).T, rtol=0, atol=1e-12)
+    with pytest.raises(ValueError):
+        s.solve(np.zeros(n + 1))
+    # projected solve without a projection; null pointers; zero right-hand sides
+    z = np.zeros(3)
+    assert fresh.lib.jgb_lin_solve_projected(fresh.handle, 1, z.ctypes.data_as(C.POINTER(C.c_double)),
+                                            x.ctypes.data_as(C.POINTER(C.c_double))) == -1
+    assert fresh.lib.jgb_lin_solve(fresh.handle, 1, None, x.ctypes.data_as(C.POINTER(C.c_double))) == -1
+    assert fresh.lib.jgb_lin_solve(fresh.handle, 0, x.ctypes.data_as(C.POINTER(C.c_double)),
+                                  x.ctypes.data_as(C.POINTER(C.c_double))) == -1
+    assert fresh.lib.jgb_lin_refactor(fresh.handle, None) == -1
+    # a projection with the wrong number of columns is refused on the host side
+    with pytest.raises(ValueError):
+        s.set_projection(sp.identity(n + 2, format="csc"))
+    s.set_projection(sp.identity(n, format="csc"))
+    b = rng.standard_normal(n)
+    np.testing.assert_allclose(s.solve_projected(b), lu.solve(b), rtol=0, atol=1e-12)
+    fresh.close()
