@@ -9,6 +9,8 @@
 #include <cstdlib>
 #include <numeric>
 #include <set>
+#include <string>
+#include <tuple>
 #include <stdexcept>
 
 namespace jgb {
@@ -59,6 +61,64 @@ std::vector<int> min_degree(int ng, std::vector<std::vector<int>> adj, const std
             heap.insert({d, u});
         }
         std::vector<int>().swap(adj[v]);
+    }
+    return order;
+}
+
+// Minimum local fill (Tinney scheme 3) on the same explicit elimination graph: the next vertex is the one whose
+// elimination creates the fewest (weighted) fill edges, ties broken by weighted degree, then by id. The fill count of a
+// vertex changes only when its neighbourhood or an edge between two of its neighbours changes, i.e. for the
+// neighbours of the eliminated vertex and their neighbours.
+std::vector<int> min_fill(int ng, std::vector<std::vector<int>> adj, const std::vector<int>& weight,
+                          size_t kExactDegree) {
+    auto has = [&](int a, int b) { return std::binary_search(adj[a].begin(), adj[a].end(), b); };
+    // exact counts only for moderate degrees: beyond that (the dense tail of the elimination, where every remaining
+    // vertex sits in a few big cliques) the quadratic count per vertex dominates the run time and no longer changes the
+    // order much, so an upper bound (all pairs missing) ranks those vertices by degree behind the exact ones
+    auto fill_of = [&](int v) {
+        long f = 0;
+        const std::vector<int>& nb = adj[v];
+        if (nb.size() > kExactDegree) {
+            long d = 0;
+            for (int u : nb) d += weight[u];
+            return (1L << 40) + d * d;
+        }
+        for (size_t i = 0; i < nb.size(); ++i)
+            for (size_t j = i + 1; j < nb.size(); ++j)
+                if (!has(nb[i], nb[j])) f += (long)weight[nb[i]] * weight[nb[j]];
+        return f;
+    };
+    auto deg_of = [&](int v) { long d = 0; for (int u : adj[v]) d += weight[u]; return d; };
+    std::vector<long> fill(ng), deg(ng);
+    std::set<std::tuple<long, long, int>> heap;
+    for (int v = 0; v < ng; ++v) { fill[v] = fill_of(v); deg[v] = deg_of(v); heap.insert({fill[v], deg[v], v}); }
+    std::vector<int> order;
+    order.reserve(ng);
+    std::vector<int> tmp, dirty;
+    std::vector<char> mark(ng, 0);
+    while (!heap.empty()) {
+        const int v = std::get<2>(*heap.begin());
+        heap.erase(heap.begin());
+        order.push_back(v);
+        const std::vector<int> nb = adj[v];
+        dirty.clear();
+        for (int u : nb) {
+            if (!mark[u]) { mark[u] = 1; dirty.push_back(u); }
+            for (int w : adj[u])
+                if (w != v && !mark[w] && adj[w].size() <= kExactDegree) { mark[w] = 1; dirty.push_back(w); }
+        }
+        for (int u : dirty) heap.erase({fill[u], deg[u], u});
+        for (int u : nb) {
+            merge_drop(adj[u], nb, u, v, tmp);
+            adj[u].swap(tmp);
+        }
+        std::vector<int>().swap(adj[v]);
+        for (int u : dirty) {
+            mark[u] = 0;
+            fill[u] = fill_of(u);
+            deg[u] = deg_of(u);
+            heap.insert({fill[u], deg[u], u});
+        }
     }
     return order;
 }
@@ -150,7 +210,11 @@ void analyse(int n, const int* colptr, const int* rowidx, const int* group, cons
                 if (v != w) sadj[v].push_back(w);
     for (auto& a : sadj) { std::sort(a.begin(), a.end()); a.erase(std::unique(a.begin(), a.end()), a.end()); }
 
-    std::vector<int> gorder = min_degree(ng, gadj, weight);
+    bool use_fill = opt.min_fill;
+    if (const char* ord = getenv("JGB_ORDER")) use_fill = std::string(ord) == "fill";     // "degree" | "fill": tuning only
+    size_t exact = (size_t)std::max(1, opt.fill_exact_degree);
+    if (const char* k = getenv("JGB_FILL_K")) exact = (size_t)std::max(1, atoi(k));
+    std::vector<int> gorder = use_fill ? min_fill(ng, gadj, weight, exact) : min_degree(ng, gadj, weight);
 
     std::vector<int> perm;
     perm.reserve(n);
