@@ -141,7 +141,9 @@ int32_t jgb_wls_batch_dev(jgb_ctx* ctx, int64_t S, const double* Z_dev, int64_t 
  * c[i] = h_i G^-1 h_i' from a sparse selected inverse of the gain factor on the device (Takahashi recurrences on the
  * elimination tree; `selectedInverse` / `rowProjection` badData.jl:287-362, 536-640), then the largest normalised
  * residual |r_i| / sqrt|1/W_ii - c_i| over the rows with a non-zero residual. Call after jgb_wls_run / the last
- * jgb_wls_increment. index: 1-based row, 0 if none; c_out: nullable [m]. */
+ * jgb_wls_increment. index: 1-based row, 0 if none; c_out: nullable [m]. `threshold` is not applied here: the call
+ * reports the maximum and its row, and the caller compares (bad.detect = maximum > threshold, badData.jl:220-222) and
+ * then removes the row(s) with jgb_wls_remove_row. */
 int32_t jgb_wls_residual_test(jgb_ctx* ctx, double threshold, double* max_normalized_residual, int64_t* index,
                               double* c_out);
 /* Row `row` (1-based) leaves the model as in badData.jl:258-282: H entries, mean and residual zeroed, type 0,
