@@ -211,3 +211,32 @@ def test_product_hdf5_case_loader_matches_fixtures():
         for k in ("bus_type", "pd", "qd", "gs", "bs", "vm", "va", "frm", "to", "r", "x", "g", "b", "tap", "shift", "status",
                   "gen_bus", "gen_p", "gen_q", "gen_vm", "gen_status", "gen_qmin", "gen_qmax"):
             assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
+def test_orderings_minimum_fill_beats_minimum_degree(monkeypatch):
+    """Both orderings of the symbolic analysis (JGB_ORDER, JGB_FILL_K) replay to the same solution; on the 10k-bus
+    Jacobian minimum local fill gives the smaller factor (the reason it is the default)."""
+    o = onr.newton_raphson(oracle_system("synthetic10k"))
+    onr.mismatch(o)
+    onr.fill_jacobian(o)
+    n = o.dim
+    grp = np.zeros(n, dtype=np.int64)
+    grp[o.pvpq[o.pvpq >= 0]] = np.flatnonzero(o.pvpq >= 0)
+    grp[o.pq[o.pq >= 0]] = np.flatnonzero(o.pq >= 0)
+    cp, rv = (o.j_colptr + 1).astype(np.int64), (o.j_rowval + 1).astype(np.int64)
+    J = onr.jacobian_csc(o)
+    out = {}
+    for order, k in (("degree", "48"), ("fill", "48"), ("fill", "16")):
+        monkeypatch.setenv("JGB_ORDER", order)
+        monkeypatch.setenv("JGB_FILL_K", k)
+        x, stats = np.zeros(n), np.zeros(8)
+        rc = jgb200.load().jgb_selfcheck_symbolic(n, ptr(cp, C.c_int64), ptr(rv, C.c_int64), ptr(o.j_nzval, C.c_double),
+                                                  ptr(grp, C.c_int64), ptr(o.mismatch, C.c_double), ptr(x, C.c_double),
+                                                  ptr(stats, C.c_double))
+        assert rc == 0
+        assert np.abs(J @ x - o.mismatch).max() <= 1e-10 * max(1.0, np.abs(o.mismatch).max())
+        out[(order, k)] = stats.copy()
+    # stats: [fronts, levels, depths, nnz(L+U), flops, max front, u_size, upd_size]
+    assert out[("fill", "48")][3] < 0.97 * out[("degree", "48")][3]
+    assert out[("fill", "48")][4] < 0.90 * out[("degree", "48")][4]
+    assert out[("fill", "16")][1] <= out[("fill", "48")][1]          # the capped rule keeps the tree shallower
