@@ -324,7 +324,7 @@ def run_ours(args):
 
     # ---- single-case rates (configs[1] and [2]), rank 0 only, a few repetitions each
     single = {}
-    if rank == 0:
+    if rank == 0 and not args.headline_only:
         reps = 5
         jgb200.set_initial_point(a)
         a._push_state()
@@ -500,7 +500,7 @@ def run_ours(args):
 
     # ---- CPU baseline: bounded sample of the same sweep on one host core (the reference is single-threaded)
     arm = CpuArm(1)
-    it_cpu, sc_cpu, busy = arm.run(elig[:96])
+    it_cpu, sc_cpu, busy = arm.run(elig[:8] if args.headline_only else elig[:96])
     rate = it_cpu / busy
     cpu = {"value": rate, "unit": UNIT, "cores": 1, "kind": "port",
            "sample": f"first {sc_cpu} outage scenarios of the sweep ({it_cpu} NR iterations, {busy:.1f} s) on 1 core; "
@@ -529,6 +529,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--headline-only", action="store_true",
+                    help="profiling runs (ncu launch lists): skip the single-case / WLS / linear extras and shorten the "
+                         "CPU baseline sample")
     ap.add_argument("--scenarios", type=int, default=10000,
                     help="outage scenarios per GPU per step (default: the whole 10 000-outage sweep of configs[3])")
     args = ap.parse_args()
