@@ -228,12 +228,12 @@ def generator_power(a: AcPowerFlow, pw: dict | None = None):
     return pg, qg
 
 
-def reactive_limit(a: AcPowerFlow) -> np.ndarray:
+def reactive_limit(a: AcPowerFlow, pw: dict | None = None) -> np.ndarray:
     """reactiveLimit!(analysis) (acPowerFlow.jl:1081-1156). Mutates `a.system` like the reference: violating
     generators are fixed at their limit and their bus becomes a demand bus (a converted slack hands over to the first
     generator bus); returns the flags (-1 / +1). Build a new analysis with newton_raphson(system) afterwards."""
     s = a.system
-    pg, qg = generator_power(a)
+    pg, qg = generator_power(a, pw)
     s.bus_type = a.bus_type.copy()
     s.slack = a.slack
     on = s.gen_status == 1

@@ -240,3 +240,30 @@ def test_orderings_minimum_fill_beats_minimum_degree(monkeypatch):
     assert out[("fill", "48")][3] < 0.97 * out[("degree", "48")][3]
     assert out[("fill", "48")][4] < 0.90 * out[("degree", "48")][4]
     assert out[("fill", "16")][1] <= out[("fill", "48")][1]          # the capped rule keeps the tree shallower
+
+
+@pytest.mark.parametrize("case", ["case14test", "case30test"])
+def test_reactive_limit_host_logic_matches_oracle(case):
+    """generator_power / reactive_limit of the host mirror (fed with the oracle's converged state instead of the device's)
+    against the oracle's restatement: outputs, violation flags, bus types, slack and the rewritten bus supply."""
+    from types import SimpleNamespace
+    from jgb200.ac_power_flow import _initialize
+    os_, ps = oracle_system(case), product_system(case)
+    o = onr.newton_raphson(os_)
+    assert onr.power_flow(o)
+    ps.model = jgb200.ac_model(ps)
+    bus_type, slack, _, _ = _initialize(ps)
+    a = SimpleNamespace(system=ps, bus_type=bus_type, slack=slack)
+    pw = jgb200.power(ps, o.vm, o.va)
+    pg, qg = jgb200.generator_power(a, pw)
+    pwo = post.powers(os_, o.mdl, o.vm, o.va)
+    opg, oqg = post.generator_powers(os_, pwo["injection_active"], pwo["injection_reactive"], o.slack)
+    np.testing.assert_allclose(pg, opg, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(qg, oqg, rtol=0, atol=1e-12)
+    violate = jgb200.reactive_limit(a, pw)
+    assert np.array_equal(violate, onr.reactive_limit(o)) and np.any(violate != 0)
+    assert np.array_equal(ps.bus_type, os_.bus_type) and ps.slack == os_.slack
+    sp_, sq_, _ = ps.supply
+    np.testing.assert_allclose(sp_, os_.supply_p, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(sq_, os_.supply_q, rtol=0, atol=1e-12)
+    np.testing.assert_allclose(ps.gen_q, os_.gen_q, rtol=0, atol=1e-12)
