@@ -213,6 +213,18 @@ int32_t jgb_profile(jgb_ctx* ctx, int32_t enable);
 int32_t jgb_selfcheck_symbolic(int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval,
                                const int64_t* group, const double* rhs, double* x, double* stats8);
 
+/* host only: the elimination tree of the analysis (preset 0 default / 1 latency / 2 throughput): pivots, order,
+ * parent (-1 = root) and number of matrix entries of every front; arrays of capacity `cap`. For tests and tuning. */
+int32_t jgb_selfcheck_tree(int64_t n, const int64_t* colptr, const int64_t* rowval, const int64_t* group, int32_t preset,
+                           int64_t cap, int64_t* nfronts, int32_t* f_k, int32_t* f_nf, int32_t* f_parent,
+                           int32_t* f_nasm);
+
+/* host only: the task partition of the batch factorisation (throughput preset) replayed on the host for one
+ * right-hand side. stats8: launches, tasks, fronts in tasks, update-block elements kept on chip, largest shared-memory
+ * need (bytes), index-blob ints, fronts, update-block elements in total. */
+int32_t jgb_selfcheck_tasks(int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                            const int64_t* group, const double* rhs, double* x, double* stats8);
+
 #ifdef __cplusplus
 }
 #endif

@@ -48,6 +48,9 @@ PROTOTYPES = {
     "jgb_stat": (C.c_double, [C.c_void_p, C.c_char_p]),
     "jgb_profile": (C.c_int32, [C.c_void_p, C.c_int32]),
     "jgb_selfcheck_symbolic": (C.c_int32, [C.c_int64, c_i64p, c_i64p, c_f64p, c_i64p, c_f64p, c_f64p, c_f64p]),
+    "jgb_selfcheck_tasks": (C.c_int32, [C.c_int64, c_i64p, c_i64p, c_f64p, c_i64p, c_f64p, c_f64p, c_f64p]),
+    "jgb_selfcheck_tree": (C.c_int32, [C.c_int64, c_i64p, c_i64p, c_i64p, C.c_int32, C.c_int64, c_i64p, c_i32p, c_i32p,
+                                       c_i32p, c_i32p]),
 }
 
 WLS_PROTOTYPES = {

@@ -503,4 +503,63 @@ int32_t jgb_selfcheck_symbolic(int64_t n, const int64_t* colptr, const int64_t* 
     }
 }
 
+int32_t jgb_selfcheck_tree(int64_t n, const int64_t* colptr, const int64_t* rowval, const int64_t* group, int32_t preset,
+                           int64_t cap, int64_t* nfronts, int32_t* f_k, int32_t* f_nf, int32_t* f_parent,
+                           int32_t* f_nasm) {
+    try {
+        if (n <= 0 || !colptr || !rowval || !nfronts) return -1;
+        std::vector<int> cp(n + 1), rv(colptr[n] - 1), grp;
+        for (int64_t i = 0; i <= n; ++i) cp[i] = (int)(colptr[i] - 1);
+        for (size_t q = 0; q < rv.size(); ++q) rv[q] = (int)(rowval[q] - 1);
+        if (group) {
+            grp.resize(n);
+            for (int64_t i = 0; i < n; ++i) grp[i] = (int)group[i];
+        }
+        jgb::Symbolic s;
+        const jgb::SymbolicOptions opt = preset == 1 ? jgb::latency_options()
+                                         : preset == 2 ? jgb::throughput_options() : jgb::SymbolicOptions();
+        jgb::analyse((int)n, cp.data(), rv.data(), group ? grp.data() : nullptr, nullptr, opt, s);
+        *nfronts = s.nfronts;
+        if (s.nfronts > cap) return -1;
+        for (int f = 0; f < s.nfronts; ++f) {
+            if (f_k) f_k[f] = s.f_k[f];
+            if (f_nf) f_nf[f] = s.f_nf[f];
+            if (f_parent) f_parent[f] = s.f_parent[f];
+            if (f_nasm) f_nasm[f] = s.f_asmptr[f + 1] - s.f_asmptr[f];
+        }
+        return 0;
+    } catch (...) {
+        return -4;
+    }
+}
+
+int32_t jgb_selfcheck_tasks(int64_t n, const int64_t* colptr, const int64_t* rowval, const double* nzval,
+                            const int64_t* group, const double* rhs, double* x, double* stats8) {
+    try {
+        if (n <= 0 || !colptr || !rowval) return -1;
+        std::vector<int> cp(n + 1), rv(colptr[n] - 1), grp;
+        for (int64_t i = 0; i <= n; ++i) cp[i] = (int)(colptr[i] - 1);
+        for (size_t q = 0; q < rv.size(); ++q) rv[q] = (int)(rowval[q] - 1);
+        if (group) {
+            grp.resize(n);
+            for (int64_t i = 0; i < n; ++i) grp[i] = (int)group[i];
+        }
+        jgb::Symbolic s;
+        jgb::analyse((int)n, cp.data(), rv.data(), group ? grp.data() : nullptr, nullptr, jgb::throughput_options(), s);
+        jgb::TaskPlan tp;
+        jgb::partition_tasks(s, jgb::task_options_from_env(), tp);
+        if (stats8) {
+            size_t smem = 0;
+            for (auto& tl : tp.launches) smem = std::max(smem, tl.smem);
+            stats8[0] = (double)tp.launches.size(); stats8[1] = tp.task_count; stats8[2] = tp.task_fronts;
+            stats8[3] = (double)tp.upd_on_chip; stats8[4] = (double)smem; stats8[5] = (double)tp.blob.size();
+            stats8[6] = s.nfronts; stats8[7] = (double)s.upd_size;
+        }
+        if (nzval && rhs && x) return jgb::host_task_factor_solve(s, tp, nzval, rhs, x);
+        return 0;
+    } catch (...) {
+        return -4;
+    }
+}
+
 }  // extern "C"

@@ -7,6 +7,7 @@
 #pragma once
 #include "common.cuh"
 #include "symbolic.hpp"
+#include "tasks.hpp"
 
 namespace jgb {
 
@@ -81,10 +82,20 @@ class MfSolver {
     std::vector<long long> zoff_host;
     int64_t factor_bytes(int S) const;     // algorithmic HBM bytes of one factor_solve (for roofline reports)
     int launches_per_solve(int S);
-    int factor_launches(int S) { plan(S); return (int)fplan.size(); }
+    int factor_launches(int S) { plan(S); return (int)(fplan.size() + tplan.size()); }
+    // batch plan statistics: fronts handled by the task kernel, tasks, update-block elements that never leave the chip
+    int task_fronts = 0, task_count = 0;
+    long long task_upd_on_chip = 0;
 
   private:
     void plan(int S);
+    void build_tasks(int S, cudaStream_t st);
+    std::vector<TaskLaunch> tplan;
+    std::vector<char> in_task;             // front is factored by a task launch (not by fplan)
+    std::vector<int> plan_levelptr, plan_fronts;   // level schedule of the fronts left to fplan
+    DevBuf<int> d_task_blob, d_plan_fronts;
+    DevBuf<int2> d_task_desc;
+    DevBuf<FrontDesc> d_plan_desc;
     int planned_S = -1;
     bool symmetric = false;
     std::vector<FactorLaunch> fplan;
