@@ -68,8 +68,9 @@ int32_t jgb_nr_run(jgb_ctx* ctx, int64_t max_iter, double tol, int64_t* iteratio
 /* S independent power flows sharing topology and symbolic factorisation (N-1 sweep: updateBranch!(status = 0),
  * powerSystem/branch.jl:313-431, each followed by powerFlow!).  Scenario s removes branch with end buses
  * out_from[s], out_to[s] (1-based bus indices, 0 = base case) whose Y-parameters nodalFromFrom / nodalFromTo /
- * nodalToFrom / nodalToTo are given in dy_re_im[s][0..7].  Every scenario starts from the state last set with
- * jgb_nr_set_state (setInitialPoint! semantics).  Outputs are S x n row-major (one row per scenario); status[s] is
+ * nodalToFrom / nodalToTo are given in dy_re_im[s][0..7].  Every scenario starts from the state that is on the
+ * device when the call is made: the one last set with jgb_nr_set_state, or the iterate a later jgb_nr_solve /
+ * jgb_nr_run left there (call jgb_nr_set_state with the start point first for setInitialPoint! semantics).  Outputs are S x n row-major (one row per scenario); status[s] is
  * 0 converged, 1 iteration cap, -3 singular (islanding outage).  *total_iterations = sum of solve! calls. */
 int32_t jgb_nr_batch(jgb_ctx* ctx, int64_t S, const int64_t* out_from, const int64_t* out_to, const double* dy_re_im,
                      int64_t max_iter, double tol, double* vm_out, double* va_out, int32_t* iterations,
@@ -136,6 +137,21 @@ int32_t jgb_wls_batch_dev(jgb_ctx* ctx, int64_t S, const double* Z_dev, int64_t 
                           double* vm_out_dev, double* va_out_dev, int32_t* iterations_dev, int8_t* status_dev,
                           double* objective_dev, int64_t* total_iterations);
 
+/* ---- in-place updates of a Gauss-Newton analysis (the Monte-Carlo / what-if loop of test/stateEstimation/reusing.jl) ---
+ * == update*!(analysis; ...) for single measurement rows (e.g. _updateWattmeter!, src/measurement/powermeter.jl:640-677,
+ * and its siblings in voltmeter.jl / ammeter.jl / pmu.jl): for every listed row (1-based) mean = status * mean,
+ * residual = 0, the row's Jacobian entries = 0, type = status * code, index, precision[row,row] = 1 / variance
+ * (precision_off = W[row,row-1] of a correlated rectangular PMU pair). NULL arrays keep the stored values. The H and
+ * gain patterns, the gather lists and the symbolic factorisation are reused; a change that needs a new pattern
+ * returns -4 (build a new context, like the reference rebuilds on a pattern change). */
+int32_t jgb_wls_update_rows(jgb_ctx* ctx, int64_t k, const int64_t* rows, const double* mean, const double* precision,
+                            const double* precision_off, const int8_t* type, const int64_t* index);
+/* == acNodalUpdate! (powerSystem/model.jl:81-110) on the model a WLS analysis reads: k stored Ybus positions */
+int32_t jgb_wls_update_y(jgb_ctx* ctx, int64_t k, const int64_t* nz_pos, const double* y_re_im, const double* yt_re_im);
+/* == acParameterUpdate! (powerSystem/model.jl:113-140): the parameters the flow / current rows of one branch read */
+int32_t jgb_wls_update_branch(jgb_ctx* ctx, int64_t branch, double conductance, double susceptance, double turns_ratio,
+                              double shift_angle, const double* admittance_re_im);
+
 /* ---- bad-data post-step -------------------------------------------------------------------------
  * == the numeric part of residualTest!(analysis; threshold) for Gauss-Newton WLS (src/stateEstimation/badData.jl:181-285):
  * c[i] = h_i G^-1 h_i' from a sparse selected inverse of the gain factor on the device (Takahashi recurrences on the
@@ -198,6 +214,29 @@ int32_t jgb_fnr_run(jgb_ctx* ctx, int64_t max_iter, double tol, int64_t* iterati
  * status 0 converged, 1 iteration cap, -3 diverged. Returns 1 if any scenario did not converge. */
 int32_t jgb_fnr_batch(jgb_ctx* ctx, int64_t R, const double* p_inj, const double* q_inj, int64_t max_iter, double tol,
                       double* vm_out, double* va_out, int32_t* iterations, int8_t* status, int64_t* total_iterations);
+
+/* ---- multi-GPU: scenario sharding with one all-gather of the converged states --------------------
+ * The reference has no distributed code: contingencies and Monte-Carlo draws are iterations of a serial user loop
+ * (updateBranch! + powerFlow!, test/powerFlow/reusing.jl:40-84; updateWattmeter!… + stateEstimation!,
+ * test/stateEstimation/reusing.jl). Here every rank (one process / context per GPU) solves its block of scenarios with
+ * jgb_nr_batch_dev / jgb_wls_batch_dev and the blocks are collected with ONE grouped NCCL all-gather over NVLink.
+ * NCCL is loaded at run time (libnccl.so.2, or the path in JGB200_NCCL_LIB); without it these calls fail with -1 and
+ * everything else works. */
+/* ncclGetUniqueId: call on one rank and hand the 128 bytes to the others by any host-side means */
+int32_t jgb_comm_unique_id(uint8_t* id128);
+/* ncclCommInitRank on the context's GPU (collective: every rank of the job calls it) */
+int32_t jgb_comm_init(jgb_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t* id128);
+/* All-gather rows_local scenarios of every rank into rank-major [nranks * rows_local] arrays: states [rows][n] (FP64),
+ * iteration counts (int32) and status bytes (int8); all pointers are DEVICE pointers, any send pointer may be NULL.
+ * rows_local must be the same on every rank (pad the last block). The collective starts when the work already enqueued
+ * on the context's stream has finished and runs on a private stream beside whatever is enqueued next; send and receive
+ * buffers must not be touched until jgb_comm_wait (or the next jgb_allgather_states, which waits first). */
+int32_t jgb_allgather_states(jgb_ctx* ctx, int64_t rows_local, int64_t n, const double* vm_dev, const double* va_dev,
+                             const int32_t* iterations_dev, const int8_t* status_dev, double* vm_all_dev,
+                             double* va_all_dev, int32_t* iterations_all_dev, int8_t* status_all_dev);
+/* host_blocking != 0: return when the all-gather has finished; 0: make the context's stream wait for it */
+int32_t jgb_comm_wait(jgb_ctx* ctx, int32_t host_blocking);
+int32_t jgb_comm_size(jgb_ctx* ctx, int32_t* rank, int32_t* nranks);     /* -1 / 0 before jgb_comm_init */
 
 /* ---- statistics for roofline reports ------------------------------------------------------------------------ */
 /* key: "nr.nnz_lu", "nr.fronts", "nr.levels", "nr.flops", "nr.max_front", "nr.launches_per_iteration",

@@ -4,7 +4,7 @@ ccall shim a JuliaGrid user loads), numerics in hand-written sm_100a CUDA behind
 """
 from ._lib import Context, JgbError, load, LIB_PATH, exported_symbols  # noqa: F401
 from .cases import PowerSystem, power_system, synthetic_grid  # noqa: F401
-from .model import AcModel, ac_model  # noqa: F401
+from .model import AcModel, ac_model, apply_branch_status  # noqa: F401
 from .ac_power_flow import (AcPowerFlow, newton_raphson, mismatch, solve, power_flow, set_initial_point,  # noqa: F401
                             set_voltage, update_branch, power_device, newtonRaphson, powerFlow, setInitialPoint, updateBranch,
                             generator_power, reactive_limit, adjust_angle, generatorPower, reactiveLimit, adjustAngle)
@@ -12,7 +12,8 @@ from .measurement import (Measurement, measurement, power, add_voltmeter, add_am
                           add_varmeter, add_pmu, ac_wls, WlsTables)
 from .ac_state_estimation import (AcStateEstimation, gauss_newton, increment, solve_se, state_estimation,  # noqa: F401
                                   set_mean, set_voltage_se, gaussNewton, stateEstimation, chi_test,
-                                  residual_test, ChiTest, ResidualTest, chiTest, residualTest)
+                                  residual_test, ChiTest, ResidualTest, chiTest, residualTest, update_voltmeter,
+                                  update_ammeter, update_wattmeter, update_varmeter, update_pmu, update_branch_se)
 from .batch import BatchResult, eligible_outages, outage_arrays, nr_batch, wls_batch  # noqa: F401
 from .linear_solver import LinearSolver  # noqa: F401
 from .dc_power_flow import DcModel, DcPowerFlow, dc_model, dc_power_flow, solve_dc, dc_batch, power_dc  # noqa: F401

@@ -45,6 +45,11 @@ PROTOTYPES = {
                                  c_f64p, c_i32p, c_i8p, c_i64p]),
     "jgb_nr_batch_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                      C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]),
+    "jgb_comm_unique_id": (C.c_int32, [C.POINTER(C.c_uint8)]),
+    "jgb_comm_init": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]),
+    "jgb_allgather_states": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64] + [C.c_void_p] * 8),
+    "jgb_comm_wait": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "jgb_comm_size": (C.c_int32, [C.c_void_p, c_i32p, c_i32p]),
     "jgb_stat": (C.c_double, [C.c_void_p, C.c_char_p]),
     "jgb_profile": (C.c_int32, [C.c_void_p, C.c_int32]),
     "jgb_selfcheck_symbolic": (C.c_int32, [C.c_int64, c_i64p, c_i64p, c_f64p, c_i64p, c_f64p, c_f64p, c_f64p]),
@@ -70,6 +75,10 @@ WLS_PROTOTYPES = {
                                   c_i8p, c_f64p, c_i64p]),
     "jgb_wls_residual_test": (C.c_int32, [C.c_void_p, C.c_double, c_f64p, c_i64p, c_f64p]),
     "jgb_wls_remove_row": (C.c_int32, [C.c_void_p, C.c_int64]),
+    "jgb_wls_update_rows": (C.c_int32, [C.c_void_p, C.c_int64, c_i64p, c_f64p, c_f64p, c_f64p, c_i8p, c_i64p]),
+    "jgb_wls_update_y": (C.c_int32, [C.c_void_p, C.c_int64, c_i64p, c_f64p, c_f64p]),
+    "jgb_wls_update_branch": (C.c_int32, [C.c_void_p, C.c_int64, C.c_double, C.c_double, C.c_double, C.c_double,
+                                          c_f64p]),
     "jgb_wls_batch_dev": (C.c_int32, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_double, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, c_i64p]),
 }

@@ -20,7 +20,7 @@ import numpy as np
 from . import _lib
 from ._lib import Context, ptr, f64, i64, i8, cplx
 from .cases import PowerSystem
-from .model import AcModel, ac_model
+from .model import AcModel, ac_model, apply_branch_status
 
 
 @dataclass
@@ -282,42 +282,12 @@ def set_voltage(a: AcPowerFlow, magnitude, angle):
 def update_branch(a: AcPowerFlow, k: int, status: int):
     """updateBranch!(analysis; label = k, status): in-place Ybus value update on the fixed pattern
     (updateBranchMain! branch.jl:313-431 + acNodalUpdate! model.jl:81-110). k is the 0-based branch index."""
-    sysm, mdl = a.system, a.system.model
-    old = int(sysm.status[k])
-    if status == old:
+    if status == int(a.system.status[k]):
         return
-    i, j = int(sysm.frm[k]), int(sysm.to[k])
-    if status == 0:
-        dff, dft, dtf, dtt = -mdl.y_ff[k], -mdl.y_ft[k], -mdl.y_tf[k], -mdl.y_tt[k]
-    else:
-        one = sysm.copy()
-        one.status[:] = 0
-        one.status[k] = 1
-        one.model = None
-        tmp = ac_model(one)
-        dff, dft, dtf, dtt = tmp.y_ff[k], tmp.y_ft[k], tmp.y_tf[k], tmp.y_tt[k]
-        mdl.admittance[k] = tmp.admittance[k]
-    pos = [mdl.position(i, i), mdl.position(j, j), mdl.position(i, j), mdl.position(j, i)]
-    # nodalMatrix: (i,i)+=ff (j,j)+=tt (i,j)+=ft (j,i)+=tf ; transpose: (j,i) position holds Y[i,j] etc.
-    mdl.nzval[pos[0]] += dff
-    mdl.nzval[pos[1]] += dtt
-    mdl.nzval[pos[2]] += dft
-    mdl.nzval[pos[3]] += dtf
-    mdl.nzval_t[pos[0]] += dff
-    mdl.nzval_t[pos[1]] += dtt
-    mdl.nzval_t[pos[3]] += dft
-    mdl.nzval_t[pos[2]] += dtf
-    if status == 0:
-        mdl.y_ff[k] = mdl.y_ft[k] = mdl.y_tf[k] = mdl.y_tt[k] = 0
-        mdl.admittance[k] = 0
-    else:
-        mdl.y_ff[k], mdl.y_ft[k], mdl.y_tf[k], mdl.y_tt[k] = dff, dft, dtf, dtt
-    sysm.status[k] = status
-    p1 = i64(np.array(pos) + 1)
-    yv = cplx(mdl.nzval[pos])
-    ytv = cplx(mdl.nzval_t[pos])
-    a.ctx.check(a.ctx.lib.jgb_nr_update_y(a.ctx.handle, 4, ptr(p1, C.c_int64), ptr(yv, C.c_double),
-                                          ptr(ytv, C.c_double)))
+    pos, yv, ytv, _ = apply_branch_status(a.system, k, status)
+    p1 = i64(pos + 1)
+    a.ctx.check(a.ctx.lib.jgb_nr_update_y(a.ctx.handle, 4, ptr(p1, C.c_int64), ptr(cplx(yv), C.c_double),
+                                          ptr(cplx(ytv), C.c_double)))
     a._branches_set = False       # Y-parameters / statuses changed: re-upload before the next power_device
 
 

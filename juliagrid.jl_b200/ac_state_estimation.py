@@ -13,6 +13,7 @@ from __future__ import annotations
 import ctypes as C
 
 import numpy as np
+import scipy.sparse as sp
 
 from ._lib import Context, ptr, f64, i64, i8, cplx
 from .ac_power_flow import Polar
@@ -222,3 +223,91 @@ gaussNewton = gauss_newton
 chiTest = chi_test
 residualTest = residual_test
 stateEstimation = state_estimation
+
+
+# ---- update*!(analysis; ...): in-place changes of single meters, reusing the gain pattern and its factorisation --------
+def _w_diag_off(t: WlsTables):
+    """Diagonal of the precision matrix and W[row, row-1] per row from the CSC tables."""
+    W = sp.csc_matrix((t.w_nzval, t.w_rowval - 1, t.w_colptr - 1), shape=(t.m, t.m))
+    d = W.diagonal()
+    off = np.zeros(t.m)
+    sub = W.diagonal(-1)
+    off[1:] = sub
+    return d, off
+
+
+def _sync_rows(a: AcStateEstimation):
+    """Rebuild the acWLS tables from the (edited) monitoring and push every row whose mean / type / index / precision
+    changed through jgb_wls_update_rows — what the reference's _update*!(analysis, idx) do row by row."""
+    old = a.method.tables
+    new = ac_wls(a.system, a.monitoring)
+    if new.m != old.m or not np.array_equal(new.h_rowval, old.h_rowval) or not np.array_equal(new.h_colptr, old.h_colptr):
+        raise ValueError("the update changes the measurement layout: build a new analysis (gauss_newton)")
+    d0, o0 = _w_diag_off(old)
+    d1, o1 = _w_diag_off(new)
+    # the analysis may hold means set with set_mean (Monte-Carlo draws): only rows whose table entries changed move
+    ch = (new.mean != old.mean) | (new.type != old.type) | (new.index != old.index) | (d0 != d1) | (o0 != o1)
+    rows = np.flatnonzero(ch)
+    if len(rows) == 0:
+        return rows
+    r1 = i64(rows + 1)
+    a.ctx.check(a.ctx.lib.jgb_wls_update_rows(a.ctx.handle, len(rows), ptr(r1, C.c_int64),
+                                              ptr(f64(new.mean[rows]), C.c_double), ptr(f64(d1[rows]), C.c_double),
+                                              ptr(f64(o1[rows]), C.c_double), ptr(i8(new.type[rows]), C.c_int8),
+                                              ptr(i64(new.index[rows]), C.c_int64)))
+    me = a.method
+    me.mean[rows] = new.mean[rows]
+    me.tables, me.type, me.index = new, new.type, new.index
+    return rows
+
+
+def _update(a: AcStateEstimation, dev: str, k: int, **fields):
+    d = getattr(a.monitoring, dev)
+    if not 0 <= k < len(d["index"]):
+        raise IndexError(f"{dev} {k} does not exist")
+    for key, val in fields.items():
+        if val is not None:
+            d[key][k] = val
+    return _sync_rows(a)
+
+
+def update_voltmeter(a: AcStateEstimation, k: int, magnitude=None, variance=None, status=None):
+    """updateVoltmeter!(analysis; label, magnitude, variance, status) (measurement/voltmeter.jl)."""
+    return _update(a, "volt", k, mean=magnitude, variance=variance, status=status)
+
+
+def update_ammeter(a: AcStateEstimation, k: int, magnitude=None, variance=None, status=None, square=None):
+    """updateAmmeter!(analysis; ...) (measurement/ammeter.jl)."""
+    return _update(a, "amp", k, mean=magnitude, variance=variance, status=status, square=square)
+
+
+def update_wattmeter(a: AcStateEstimation, k: int, active=None, variance=None, status=None):
+    """updateWattmeter!(analysis; label, active, variance, status) (measurement/powermeter.jl:608-677)."""
+    return _update(a, "watt", k, mean=active, variance=variance, status=status)
+
+
+def update_varmeter(a: AcStateEstimation, k: int, reactive=None, variance=None, status=None):
+    """updateVarmeter!(analysis; ...) (measurement/powermeter.jl)."""
+    return _update(a, "var", k, mean=reactive, variance=variance, status=status)
+
+
+def update_pmu(a: AcStateEstimation, k: int, magnitude=None, angle=None, variance_magnitude=None, variance_angle=None,
+               status_magnitude=None, status_angle=None, polar=None, correlated=None, square=None):
+    """updatePmu!(analysis; ...) (measurement/pmu.jl). Switching `correlated` on for a PMU that was built without it
+    adds an off-diagonal precision entry, i.e. a new gain pattern: the library answers -4 and a new analysis is needed."""
+    return _update(a, "pmu", k, mag_mean=magnitude, ang_mean=angle, mag_variance=variance_magnitude,
+                   ang_variance=variance_angle, mag_status=status_magnitude, ang_status=status_angle, polar=polar,
+                   correlated=correlated, square=square)
+
+
+def update_branch_se(a: AcStateEstimation, k: int, status: int):
+    """updateBranch!(analysis; label, status) on a state-estimation analysis (powerSystem/branch.jl:453-475): the Ybus
+    values the injection rows read and the parameters the flow rows of the branch read change in place; meters on a
+    branch taken out of service must be switched off by the caller (update_*meter(status=0)), as in the reference."""
+    from .model import apply_branch_status
+    s = a.system
+    pos, y, yt, adm = apply_branch_status(s, k, status)
+    a.ctx.check(a.ctx.lib.jgb_wls_update_y(a.ctx.handle, len(pos), ptr(i64(pos + 1), C.c_int64), ptr(cplx(y), C.c_double),
+                                           ptr(cplx(yt), C.c_double)))
+    a.ctx.check(a.ctx.lib.jgb_wls_update_branch(a.ctx.handle, k + 1, float(s.g[k]), float(s.b[k]), float(s.tap[k]),
+                                                float(s.shift[k]), ptr(cplx(np.array([adm])), C.c_double)))

@@ -93,13 +93,22 @@ def outage_arrays(system: PowerSystem, branches):
     return of, ot, np.ascontiguousarray(dy).view(np.float64).reshape(len(ks), 8)
 
 
-def nr_batch(a: AcPowerFlow, branches, iteration: int = 20, tolerance: float = 1e-8) -> BatchResult:
-    """One powerFlow! per outage scenario (branch index, -1 = base case), all from the analysis' start point."""
+def nr_batch(a: AcPowerFlow, branches, iteration: int = 20, tolerance: float = 1e-8,
+             warm_start: bool = False) -> BatchResult:
+    """One powerFlow! per outage scenario (branch index, -1 = base case). Every scenario starts from the analysis' start
+    point (setInitialPoint! before each powerFlow!, like fnr_batch); with warm_start=True from analysis.voltage as it
+    stands — after power_flow() that is the converged base case, the reference's behaviour when the user loop does not
+    call setInitialPoint!. The analysis' own voltages are left untouched either way."""
     system = a.system
     S = len(branches)
     of, ot, dy = outage_arrays(system, branches)
-    if a._state_dirty:
-        a._push_state()
+    if warm_start:
+        if a._state_dirty:
+            a._push_state()
+    else:
+        a.ctx.check(a.ctx.lib.jgb_nr_set_state(a.ctx.handle, ptr(f64(a._initial[0]), C.c_double),
+                                               ptr(f64(a._initial[1]), C.c_double)))
+        a._state_dirty = True           # the device holds the start point now, not analysis.voltage
     vm, va = np.empty((S, system.n)), np.empty((S, system.n))
     it, st = np.empty(S, dtype=np.int32), np.empty(S, dtype=np.int8)
     tot = C.c_int64(0)

@@ -5,6 +5,7 @@
 #include <memory>
 #include <string>
 
+#include "comm.cuh"
 #include "common.cuh"
 #include "fnr.cuh"
 #include "lin.cuh"
@@ -22,6 +23,7 @@ struct jgb_ctx {
     std::unique_ptr<jgb::NrContext> nr;
     std::unique_ptr<jgb::LinContext> lin;
     std::unique_ptr<jgb::FnrContext> fnr;
+    std::unique_ptr<jgb::CommContext> comm;
 #ifdef JGB_WITH_WLS
     std::unique_ptr<jgb::WlsContext> wls;
 #endif
@@ -54,6 +56,15 @@ int32_t guarded(jgb_ctx* ctx, F&& fn) {
         ctx->err = e.what();
         return -4;
     }
+}
+
+// Batch kernels put the scenario tiles in gridDim.y (<= 65535 tiles of 32): reject what cannot be launched instead of
+// failing with a CUDA launch error, and the iteration cap / tolerance like the single-case entry points do.
+constexpr int64_t kMaxBatch = 65535LL * 32;
+void check_batch_args(const char* who, int64_t S, int64_t max_iter, double tol) {
+    if (S <= 0 || S > kMaxBatch)
+        throw std::invalid_argument(std::string(who) + ": batch size must be in 1.." + std::to_string(kMaxBatch));
+    if (max_iter < 0 || !(tol > 0)) throw std::invalid_argument(std::string(who) + ": max_iter >= 0 and tol > 0 required");
 }
 
 jgb::NrContext& nr_of(jgb_ctx* ctx) {
@@ -217,6 +228,7 @@ int32_t jgb_nr_batch(jgb_ctx* ctx, int64_t S, const int64_t* out_from, const int
                      int8_t* status, int64_t* total_iterations) {
     return guarded(ctx, [&] {
         if (!vm_out || !va_out) throw std::invalid_argument("nr_batch: null output");
+        check_batch_args("nr_batch", S, max_iter, tol);
         return nr_of(ctx).batch(S, out_from, out_to, dy, false, max_iter, tol, vm_out, va_out, iterations, status,
                                 false, total_iterations);
     });
@@ -227,6 +239,7 @@ int32_t jgb_nr_batch_dev(jgb_ctx* ctx, int64_t S, const int64_t* out_from, const
                          int8_t* status, int64_t* total_iterations) {
     return guarded(ctx, [&] {
         if (!vm_out || !va_out || !iterations || !status) throw std::invalid_argument("nr_batch_dev: null output");
+        check_batch_args("nr_batch_dev", S, max_iter, tol);
         return nr_of(ctx).batch(S, out_from, out_to, dy, true, max_iter, tol, vm_out, va_out, iterations, status,
                                 true, total_iterations);
     });
@@ -317,6 +330,7 @@ int32_t jgb_wls_batch(jgb_ctx* ctx, int64_t S, const double* Z, int64_t max_iter
                       int64_t* total_iterations) {
     return guarded(ctx, [&] {
         if (!vm_out || !va_out) throw std::invalid_argument("wls_batch: null output");
+        check_batch_args("wls_batch", S, max_iter, tol);
         return wls_of(ctx).batch(S, Z, false, max_iter, tol, vm_out, va_out, iterations, status, objective, false,
                                  total_iterations);
     });
@@ -327,6 +341,7 @@ int32_t jgb_wls_batch_dev(jgb_ctx* ctx, int64_t S, const double* Z, int64_t max_
                           int64_t* total_iterations) {
     return guarded(ctx, [&] {
         if (!vm_out || !va_out || !iterations || !status) throw std::invalid_argument("wls_batch_dev: null output");
+        check_batch_args("wls_batch_dev", S, max_iter, tol);
         return wls_of(ctx).batch(S, Z, true, max_iter, tol, vm_out, va_out, iterations, status, objective, true,
                                  total_iterations);
     });
@@ -347,6 +362,29 @@ int32_t jgb_profile(jgb_ctx* ctx, int32_t enable) {
 int32_t jgb_wls_residual_test(jgb_ctx* ctx, double threshold, double* max_normalized_residual, int64_t* index,
                               double* c_out) {
     return guarded(ctx, [&] { wls_of(ctx).residual_test(threshold, max_normalized_residual, index, c_out); return 0; });
+}
+
+int32_t jgb_wls_update_rows(jgb_ctx* ctx, int64_t k, const int64_t* rows, const double* mean, const double* precision,
+                            const double* precision_off, const int8_t* type, const int64_t* index) {
+    return guarded(ctx, [&] {
+        wls_of(ctx).update_rows(k, rows, mean, precision, precision_off, type, index);
+        return 0;
+    });
+}
+
+int32_t jgb_wls_update_y(jgb_ctx* ctx, int64_t k, const int64_t* nz_pos, const double* y_re_im, const double* yt_re_im) {
+    return guarded(ctx, [&] {
+        wls_of(ctx).update_y(k, nz_pos, y_re_im, yt_re_im);
+        return 0;
+    });
+}
+
+int32_t jgb_wls_update_branch(jgb_ctx* ctx, int64_t branch, double conductance, double susceptance, double turns_ratio,
+                              double shift_angle, const double* admittance_re_im) {
+    return guarded(ctx, [&] {
+        wls_of(ctx).update_branch(branch, conductance, susceptance, turns_ratio, shift_angle, admittance_re_im);
+        return 0;
+    });
 }
 
 int32_t jgb_wls_remove_row(jgb_ctx* ctx, int64_t row) {
@@ -453,8 +491,55 @@ int32_t jgb_fnr_run(jgb_ctx* ctx, int64_t max_iter, double tol, int64_t* iterati
 int32_t jgb_fnr_batch(jgb_ctx* ctx, int64_t R, const double* p_inj, const double* q_inj, int64_t max_iter, double tol,
                       double* vm_out, double* va_out, int32_t* iterations, int8_t* status, int64_t* total_iterations) {
     return guarded(ctx, [&] {
-        if (max_iter < 0 || !(tol > 0)) throw std::invalid_argument("fnr_batch: max_iter >= 0 and tol > 0 required");
+        check_batch_args("fnr_batch", R, max_iter, tol);
         return fnr_of(ctx).batch(R, p_inj, q_inj, max_iter, tol, vm_out, va_out, iterations, status, total_iterations);
+    });
+}
+
+
+/* ---- multi-GPU ------------------------------------------------------------------------------------------------ */
+int32_t jgb_comm_unique_id(uint8_t* id128) {
+    try {
+        if (!id128) return -1;
+        jgb::CommContext::unique_id(id128);
+        return 0;
+    } catch (const std::exception& e) {
+        g_create_error = e.what();
+        return -4;
+    }
+}
+
+int32_t jgb_comm_init(jgb_ctx* ctx, int32_t rank, int32_t nranks, const uint8_t* id128) {
+    return guarded(ctx, [&] {
+        if (!ctx->comm) ctx->comm = std::make_unique<jgb::CommContext>(ctx->stream);
+        ctx->comm->init(rank, nranks, id128);
+        return 0;
+    });
+}
+
+int32_t jgb_allgather_states(jgb_ctx* ctx, int64_t rows_local, int64_t n, const double* vm_dev, const double* va_dev,
+                             const int32_t* iterations_dev, const int8_t* status_dev, double* vm_all_dev,
+                             double* va_all_dev, int32_t* iterations_all_dev, int8_t* status_all_dev) {
+    return guarded(ctx, [&] {
+        if (!ctx->comm) throw std::logic_error("allgather_states: jgb_comm_init has not been called");
+        ctx->comm->allgather_states(rows_local, n, vm_dev, va_dev, iterations_dev, status_dev, vm_all_dev, va_all_dev,
+                                    iterations_all_dev, status_all_dev);
+        return 0;
+    });
+}
+
+int32_t jgb_comm_wait(jgb_ctx* ctx, int32_t host_blocking) {
+    return guarded(ctx, [&] {
+        if (ctx->comm) ctx->comm->wait(host_blocking != 0);
+        return 0;
+    });
+}
+
+int32_t jgb_comm_size(jgb_ctx* ctx, int32_t* rank, int32_t* nranks) {
+    return guarded(ctx, [&] {
+        if (rank) *rank = ctx->comm ? ctx->comm->rank : -1;
+        if (nranks) *nranks = ctx->comm ? ctx->comm->nranks : 0;
+        return 0;
     });
 }
 

@@ -34,12 +34,12 @@ fnr_mismatch_kernel(FnrDev d, int q_only) {
             if (!q_only) {
                 const double f = cur_p - d.pinj[(size_t)i * d.R + r] * vinv;
                 d.mp[(size_t)d.pvpq[i] * d.R + r] = f;
-                ap = fabs(f);
+                ap = (f != f) ? INFINITY : fabs(f);      // fmax() drops NaN operands: a diverged run must not read as converged
             }
             if (is_pq) {
                 const double f = q_only ? cur_q - d.qinj[(size_t)i * d.R + r] / Vi : cur_q - d.qinj[(size_t)i * d.R + r] * vinv;
                 d.mq[(size_t)d.pq[i] * d.R + r] = f;
-                aq = fabs(f);
+                aq = (f != f) ? INFINITY : fabs(f);
             }
         }
     }
@@ -70,7 +70,7 @@ __global__ void fnr_check_kernel(FnrDev d, int Rreal, double tol, int max_iter) 
     if (tol < 0.0) return;
     if (r >= Rreal) { d.active[r] = 0; return; }
     if (sp < tol && sq < tol) { d.active[r] = 0; d.status[r] = 0; return; }
-    if (!(sp == sp) || !(sq == sq)) { d.active[r] = 0; d.status[r] = -3; return; }
+    if (!(sp <= 1.79e308) || !(sq <= 1.79e308)) { d.active[r] = 0; d.status[r] = -3; return; }   // NaN or Inf mismatch: diverged
     if (d.iters[r] == max_iter) { d.active[r] = 0; d.status[r] = 1; return; }
     atomicAdd(d.remaining, 1);
 }
@@ -305,7 +305,7 @@ int FnrContext::batch(int64_t Rreal64, const double* pinj, const double* qinj, i
                       double* vm_out, double* va_out, int32_t* iters_out, int8_t* status_out, int64_t* total) {
     if (!have_state) throw std::logic_error("set_state must precede batch (start point of every scenario)");
     if (Rreal64 <= 0 || !pinj || !qinj || !vm_out || !va_out) throw std::invalid_argument("fnr_batch: null or empty input");
-    if (Rreal64 > (1 << 22)) throw std::invalid_argument("fnr_batch: too many scenarios");
+    if (Rreal64 > 65535LL * 32) throw std::invalid_argument("fnr_batch: too many scenarios");
     const int Rreal = (int)Rreal64, Rp = ceil_div(Rreal, 32) * 32;
     alloc(Rp);
     FnrDev d = view();

@@ -204,7 +204,7 @@ void LinContext::solve(int64_t R, const double* in, bool dev_in, double* out, bo
     if (n == 0) throw std::logic_error("jgb_lin_setup has not been called on this context");
     if (projected && m == 0) throw std::logic_error("jgb_lin_projection has not been called on this context");
     if (R <= 0 || !in || !out) throw std::invalid_argument("lin_solve: null or empty input");
-    if (R > (1 << 24)) throw std::invalid_argument("lin_solve: too many right-hand sides");
+    if (R > 65535LL * 32) throw std::invalid_argument("lin_solve: too many right-hand sides");
     const int Rp = (int)((R + 31) / 32 * 32), nn = (int)n;
     const int rows_in = projected ? (int)m : nn;
     const double* din = in;

@@ -760,6 +760,8 @@ double NrContext::stat(const std::string& key) {
         if (key == "nr.batch.nnz_lu") return (double)b.nnz_lu;
         if (key == "nr.batch.max_front") return b.max_front;
         if (key == "nr.batch.factor_launches") return solver_batch.factor_launches(32);
+        if (key == "nr.batch.task_fronts") { solver_batch.factor_launches(32); return solver_batch.task_fronts; }
+        if (key == "nr.batch.task_upd_on_chip") { solver_batch.factor_launches(32); return (double)solver_batch.task_upd_on_chip; }
         if (key == "nr.batch.launches_per_solve") return solver_batch.launches_per_solve(32);
         return -1.0;
     }

@@ -673,7 +673,15 @@ void WlsContext::setup(int64_t n_, int64_t m_, int64_t slack_, const int64_t* hc
     iteration = 0;
     have_mean = have_state = false;
     batch_S = 0;
-    // host copies for the lazily built bad-data lists (residual_test)
+    // host copies for row updates (update_rows) and the lazily built bad-data lists (residual_test)
+    h_rowent = rowent;
+    h_ycolptr = ycolptr;
+    h_yrow = yrow;
+    h_brfrom = br_from;
+    h_brto = br_to;
+    h_type.assign(type, type + m);
+    h_index = idx0;
+    h_woff = woff;
     h_slotptr = slotptr;
     h_slotpos = slotpos;
     h_wdiag = wdiag;
@@ -1039,6 +1047,121 @@ void WlsContext::residual_test(double threshold, double* max_rn, int64_t* index,
     if (c_out) std::copy(c.begin(), c.end(), c_out);
 }
 
+// Slots of one measurement row in the semantic order the rows kernel expects (the same rules as in setup)
+static void row_slots(int code, int k, int row, int n, const std::vector<std::vector<std::pair<int, int>>>& rowent,
+                      const std::vector<int>& ycolptr, const std::vector<int>& yrow, const std::vector<int>& brf,
+                      const std::vector<int>& brt, std::vector<int>& out) {
+    auto hpos = [&](int col) -> int {
+        for (auto& e : rowent[row])
+            if (e.first == col) return e.second;
+        throw std::runtime_error("wls_update_rows: the H pattern does not hold the entry this measurement type needs");
+    };
+    out.clear();
+    if (code == 1 || code == 12) out.push_back(hpos(k + n));
+    else if (code == 13) out.push_back(hpos(k));
+    else if (code == 6 || code == 9) {
+        for (int q = ycolptr[k]; q < ycolptr[k + 1]; ++q) { out.push_back(hpos(yrow[q])); out.push_back(hpos(yrow[q] + n)); }
+    } else if (code == 16 || code == 17) { out.push_back(hpos(k)); out.push_back(hpos(k + n)); }
+    else if (code != 0) {
+        const int i = brf[k], j = brt[k];
+        out.push_back(hpos(i)); out.push_back(hpos(i + n)); out.push_back(hpos(j)); out.push_back(hpos(j + n));
+    }
+}
+
+// update*!(analysis; ...) on a Gauss-Newton analysis (e.g. _updateWattmeter!, src/measurement/powermeter.jl:640-677 and
+// its siblings for the other meters): mean = status * mean, residual = 0, the row's Jacobian entries = 0, type =
+// status * code, precision[idx, idx] = 1 / variance. The gain pattern and the symbolic factorisation are reused.
+void WlsContext::update_rows(int64_t k, const int64_t* rows, const double* mean, const double* precision,
+                             const double* precision_off, const int8_t* type, const int64_t* index) {
+    if (!m) throw std::logic_error("wls_setup has not been called");
+    if (k <= 0 || !rows) throw std::invalid_argument("wls_update_rows: null or empty input");
+    bool slots_changed = false;
+    std::vector<int> slots;
+    for (int64_t e = 0; e < k; ++e) {
+        if (rows[e] < 1 || rows[e] > m) throw std::invalid_argument("wls_update_rows: row out of range");
+        const int r = (int)rows[e] - 1;
+        const int code = type ? type[e] : h_type[r];
+        const int idx = index ? (int)index[e] - 1 : h_index[r];
+        if (code < 0 || code > 21) throw std::invalid_argument("wls_update_rows: unknown measurement code");
+        const bool bus_row = code == 1 || code == 6 || code == 9 || code == 12 || code == 13 || code == 16 || code == 17;
+        if (code != 0 && (idx < 0 || idx >= (bus_row ? n : nbr)))
+            throw std::invalid_argument("wls_update_rows: measurement index out of range");
+        if (precision_off && precision_off[e] != 0.0 && h_woff[r] == 0.0)
+            throw std::runtime_error("wls_update_rows: a new off-diagonal precision entry changes the gain pattern (-4)");
+        if (precision && !(precision[e] == precision[e])) throw std::invalid_argument("wls_update_rows: NaN precision");
+        // the row's slot list follows its type: rebuild it when the type or location changes
+        row_slots(code, idx, r, n, h_rowent, h_ycolptr, h_yrow, h_brfrom, h_brto, slots);
+        std::vector<int> old(h_slotpos.begin() + h_slotptr[r], h_slotpos.begin() + h_slotptr[r + 1]);
+        // Jacobian entries of the row: zeroed (constant entries of codes 1 / 12 / 13 are set again below)
+        for (auto& ent : h_rowent[r]) h_const[ent.second] = 0.0;
+        if (slots != old) {
+            slots_changed = true;
+            pending_slots[r] = slots;
+        }
+        if (code == 1 || code == 12 || code == 13) h_const[slots[0]] = 1.0;
+        h_type[r] = (int8_t)code;
+        h_index[r] = idx;
+        if (precision) h_wdiag[r] = precision[e];
+        if (precision_off) h_woff[r] = precision_off[e];
+    }
+    if (slots_changed) {     // rare: a row changed its type class or came back into service — rebuild the flat lists
+        std::vector<int> sp(m + 1, 0), pos;
+        pos.reserve(h_slotpos.size() + 16);
+        for (int r = 0; r < m; ++r) {
+            auto it = pending_slots.find(r);
+            if (it != pending_slots.end()) pos.insert(pos.end(), it->second.begin(), it->second.end());
+            else pos.insert(pos.end(), h_slotpos.begin() + h_slotptr[r], h_slotpos.begin() + h_slotptr[r + 1]);
+            sp[r + 1] = (int)pos.size();
+        }
+        pending_slots.clear();
+        h_slotptr.swap(sp);
+        h_slotpos.swap(pos);
+        d_slotptr.upload(h_slotptr, stream);
+        d_slotpos.upload(h_slotpos, stream);
+        have_pairs = false;
+    }
+    // per-row scalars and the row's Jacobian entries on the device
+    for (int64_t e = 0; e < k; ++e) {
+        const int r = (int)rows[e] - 1;
+        const signed char tc = (signed char)h_type[r];
+        JGB_CUDA(cudaMemcpyAsync(d_type.p + r, &h_type[r], 1, cudaMemcpyHostToDevice, stream));
+        JGB_CUDA(cudaMemcpyAsync(d_index.p + r, &h_index[r], sizeof(int), cudaMemcpyHostToDevice, stream));
+        JGB_CUDA(cudaMemcpyAsync(d_wdiag.p + r, &h_wdiag[r], sizeof(double), cudaMemcpyHostToDevice, stream));
+        JGB_CUDA(cudaMemcpyAsync(d_woff.p + r, &h_woff[r], sizeof(double), cudaMemcpyHostToDevice, stream));
+        if (mean) JGB_CUDA(cudaMemcpyAsync(d_z.p + r, &mean[e], sizeof(double), cudaMemcpyHostToDevice, stream));
+        JGB_CUDA(cudaMemsetAsync(d_res.p + r, 0, sizeof(double), stream));
+        for (auto& ent : h_rowent[r])
+            JGB_CUDA(cudaMemcpyAsync(d_hval.p + ent.second, &h_const[ent.second], sizeof(double), cudaMemcpyHostToDevice,
+                                     stream));
+        (void)tc;
+    }
+    JGB_CUDA(cudaStreamSynchronize(stream));
+    have_pairs = have_pairs && !precision;     // the projection lists cache 1 / W_ii
+}
+
+// acNodalUpdate! on the model a WLS analysis reads (powerSystem/model.jl:81-110): value-only Ybus update
+void WlsContext::update_y(int64_t k, const int64_t* pos, const double* y, const double* yt) {
+    if (!m) throw std::logic_error("wls_setup has not been called");
+    if (k <= 0 || !pos || !y || !yt) throw std::invalid_argument("wls_update_y: null or empty input");
+    for (int64_t e = 0; e < k; ++e) {
+        if (pos[e] < 1 || pos[e] > nnzy) throw std::invalid_argument("wls_update_y: position out of range");
+        JGB_CUDA(cudaMemcpyAsync(d_y.p + (pos[e] - 1), y + 2 * e, sizeof(double2), cudaMemcpyHostToDevice, stream));
+        JGB_CUDA(cudaMemcpyAsync(d_yt.p + (pos[e] - 1), yt + 2 * e, sizeof(double2), cudaMemcpyHostToDevice, stream));
+    }
+    JGB_CUDA(cudaStreamSynchronize(stream));
+}
+
+// acParameterUpdate! (powerSystem/model.jl:113-140) for the flow / current rows of one branch
+void WlsContext::update_branch(int64_t branch1, double cond, double susc, double tap, double shift, const double* adm) {
+    if (!m) throw std::logic_error("wls_setup has not been called");
+    if (branch1 < 1 || branch1 > nbr || !adm) throw std::invalid_argument("wls_update_branch: bad branch index or null input");
+    const int b = (int)branch1 - 1;
+    const double v[6] = {adm[0], adm[1], 0.5 * cond, 0.5 * susc, 1.0 / tap, shift};
+    double* dst[6] = {d_br_g.p + b, d_br_b.p + b, d_br_gsi.p + b, d_br_bsi.p + b, d_br_tinv.p + b, d_br_phi.p + b};
+    for (int q = 0; q < 6; ++q) JGB_CUDA(cudaMemcpyAsync(dst[q], &v[q], sizeof(double), cudaMemcpyHostToDevice, stream));
+    JGB_CUDA(cudaStreamSynchronize(stream));
+}
+
 void WlsContext::remove_row(int64_t row1) {
     if (!m) throw std::logic_error("wls_setup has not been called");
     if (row1 < 1 || row1 > m) throw std::invalid_argument("wls_remove_row: row out of range");
@@ -1047,6 +1170,7 @@ void WlsContext::remove_row(int64_t row1) {
                                                d_z.p, d_type.p);
     ++launches;
     for (int t = h_slotptr[r]; t < h_slotptr[r + 1]; ++t) h_const[h_slotpos[t]] = 0.0;
+    h_type[r] = 0;
     JGB_CUDA(cudaGetLastError());
     JGB_CUDA(cudaStreamSynchronize(stream));
     iteration = 0;

@@ -2,6 +2,9 @@
 // pattern of H'WH, multifrontal solve, state update. Stands in for src/stateEstimation/acStateEstimation.jl
 // :261-583 (normalEquation!), :878-904 (increment!), :1035-1047 (solve!), :1286-1329 (stateEstimation!).
 #pragma once
+#include <map>
+#include <utility>
+
 #include "common.cuh"
 #include "solver.cuh"
 
@@ -77,6 +80,12 @@ class WlsContext {
     // monitoring bookkeeping stays with the host. index is 1-based, 0 when every residual is zero.
     void residual_test(double threshold, double* max_rn, int64_t* index, double* c_out);
     void remove_row(int64_t row);              // 1-based; the row leaves the model (type 0)
+    // update*!(analysis; ...) of single measurement rows, value-only Ybus and branch-parameter updates: the gain pattern,
+    // its gather lists and the symbolic factorisation are reused (pattern changes throw -> rebuild the context)
+    void update_rows(int64_t k, const int64_t* rows, const double* mean, const double* precision,
+                     const double* precision_off, const int8_t* type, const int64_t* index);
+    void update_y(int64_t k, const int64_t* pos, const double* y, const double* yt);
+    void update_branch(int64_t branch, double cond, double susc, double tap, double shift, const double* adm);
     double stat(const std::string& key);
 
     int n = 0, m = 0, slack = -1, nnzh = 0, nnzg = 0, nbr = 0, nnzy = 0;
@@ -119,7 +128,11 @@ class WlsContext {
     // bad-data lists (built on the first residual_test)
     void build_pairs();
     bool have_pairs = false;
-    std::vector<int> h_slotptr, h_slotpos, h_poscol;
+    std::vector<int> h_slotptr, h_slotpos, h_poscol, h_ycolptr, h_yrow, h_brfrom, h_brto, h_index;
+    std::vector<int8_t> h_type;
+    std::vector<double> h_woff;
+    std::vector<std::vector<std::pair<int, int>>> h_rowent;     // per row: (column, CSC position) of its H entries
+    std::map<int, std::vector<int>> pending_slots;
     std::vector<double> h_wdiag;
     DevBuf<int> d_pair_ptr, d_pair_pa, d_pair_pb;
     DevBuf<long long> d_pair_z;

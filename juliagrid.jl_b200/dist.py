@@ -88,3 +88,53 @@ def gather_batch_result_async(vm, va, iterations, status, group=None) -> Pending
     works = [dist.all_gather_into_tensor(state, src, group=group, async_op=True),
              dist.all_gather_into_tensor(meta, meta_src, group=group, async_op=True)]
     return PendingGather(works, state, meta, vm.shape[1], keep=(src, meta_src))
+
+
+# ---- the library's own collective (jgb_comm_init / jgb_allgather_states, include/jgb200.h) ---------------------------
+def comm_init(ctx, rank: int | None = None, world: int | None = None, group=None):
+    """jgb_comm_init on every rank of the job. Rank 0 draws the NCCL unique id (jgb_comm_unique_id) and
+    torch.distributed — any backend, it only carries 128 bytes of host data — hands it to the others. With world == 1
+    no process group is needed."""
+    import ctypes as C
+    import torch.distributed as dist
+    have_pg = dist.is_available() and dist.is_initialized()
+    if rank is None:
+        rank = dist.get_rank(group) if have_pg else 0
+    if world is None:
+        world = dist.get_world_size(group) if have_pg else 1
+    ident = (C.c_uint8 * 128)()
+    if rank == 0:
+        rc = ctx.lib.jgb_comm_unique_id(ident)
+        if rc != 0:
+            raise RuntimeError("jgb_comm_unique_id failed: " + ctx.lib.jgb_last_error(None).decode())
+    if world > 1:
+        box = [bytes(ident)]
+        dist.broadcast_object_list(box, src=0, group=group)
+        ident = (C.c_uint8 * 128).from_buffer_copy(box[0])
+    ctx.check(ctx.lib.jgb_comm_init(ctx.handle, rank, world, ident))
+    return rank, world
+
+
+def allgather_states(ctx, vm, va, iterations, status, out=None):
+    """jgb_allgather_states on torch CUDA tensors: vm / va [rows][n] float64, iterations int32, status int8 (any may be
+    None). Returns (vm_all, va_all, iterations_all, status_all) of shape [world * rows, ...]; the collective is in flight
+    on the library's private stream — call comm_wait(ctx) (or the next allgather_states) before touching the buffers."""
+    import ctypes as C
+    import torch
+    r, w = C.c_int32(0), C.c_int32(0)
+    ctx.check(ctx.lib.jgb_comm_size(ctx.handle, C.byref(r), C.byref(w)))
+    world = w.value
+    first = next(t for t in (vm, va, iterations, status) if t is not None)
+    rows = first.shape[0]
+    n = vm.shape[1] if vm is not None else (va.shape[1] if va is not None else 1)
+    if out is None:
+        out = tuple(None if t is None else torch.empty((world * rows,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+                    for t in (vm, va, iterations, status))
+    P = lambda t: C.c_void_p(t.data_ptr()) if t is not None else None
+    ctx.check(ctx.lib.jgb_allgather_states(ctx.handle, rows, n, P(vm), P(va), P(iterations), P(status), P(out[0]),
+                                           P(out[1]), P(out[2]), P(out[3])))
+    return out
+
+
+def comm_wait(ctx, host_blocking: bool = True):
+    ctx.check(ctx.lib.jgb_comm_wait(ctx.handle, 1 if host_blocking else 0))

@@ -3,14 +3,15 @@
 #
 # Host code only. It reads the reference's own structures (`PowerSystem`, `Measurement`, the tables `acWLS` builds)
 # and passes their arrays — Float64 / Int64 (1-based) / Int8 / ComplexF64 — straight to the C ABI of include/jgb200.h.
-# NOTE: Julia is not installed in the build image, so this file has been reviewed by eye only; the same ABI is
-# exercised by the Python host mirror (juliagrid.jl_b200/*.py) in the test-suite.
+# NOTE: Julia is not installed in the build image or on the GPU box, so this file has NEVER BEEN EXECUTED: it is a
+# reviewed-by-eye sketch of the binding a maintainer adds (INTEGRATION.md), not a tested artefact. The same ABI, call
+# for call, is exercised by the Python host mirror (juliagrid.jl_b200/*.py) and by tests/abi_c_test.c in the test-suite.
 module JuliaGridB200
 
 using JuliaGrid
 using SparseArrays
 import JuliaGrid: newtonRaphson, gaussNewton, mismatch!, solve!, increment!, powerFlow!, stateEstimation!,
-    setInitialPoint!, AC, Polar, PowerSystem, Measurement, Normal
+    setInitialPoint!, power!, current!, AC, Polar, PowerSystem, Measurement, Normal
 
 const libjgb = get(ENV, "JGB200_LIB", joinpath(@__DIR__, "..", "libjgb200.so"))
 
@@ -48,11 +49,14 @@ mutable struct NewtonRaphsonB200
 end
 
 mutable struct AcPowerFlowB200 <: AC
-    voltage::Polar
+    voltage::Polar                 # the SAME objects as reference.voltage / power / current
     power::JuliaGrid.AcPower
     current::JuliaGrid.AcCurrent
     method::NewtonRaphsonB200
     system::PowerSystem
+    reference::Any                 # the reference's own AcPowerFlow{NewtonRaphson{LU}}: start point, power!, current!
+    deviceMagnitude::Vector{Float64}   # what the device holds; analysis.voltage is pushed when it differs
+    deviceAngle::Vector{Float64}
 end
 
 function newtonRaphson(system::PowerSystem, ::Type{B200}; device::Integer = 0)
@@ -77,17 +81,45 @@ function newtonRaphson(system::PowerSystem, ::Type{B200}; device::Integer = 0)
     check(ctx, ccall((:jgb_nr_set_injection, libjgb), Int32,
         (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
         ctx.handle, bus.supply.active, bus.supply.reactive, bus.demand.active, bus.demand.reactive))
-    analysis = AcPowerFlowB200(ref.voltage, ref.power, ref.current, m, system)
+    analysis = AcPowerFlowB200(ref.voltage, ref.power, ref.current, m, system, ref,
+        similar(ref.voltage.magnitude), similar(ref.voltage.angle))
     pushState!(analysis)
     return analysis
 end
 
-pushState!(a::AcPowerFlowB200) = check(a.method.ctx, ccall((:jgb_nr_set_state, libjgb), Int32,
-    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
-pullState!(a::AcPowerFlowB200) = check(a.method.ctx, ccall((:jgb_nr_get_state, libjgb), Int32,
-    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
+function pushState!(a::AcPowerFlowB200)
+    check(a.method.ctx, ccall((:jgb_nr_set_state, libjgb), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
+    copyto!(a.deviceMagnitude, a.voltage.magnitude)
+    copyto!(a.deviceAngle, a.voltage.angle)
+    return nothing
+end
+function pullState!(a::AcPowerFlowB200)
+    check(a.method.ctx, ccall((:jgb_nr_get_state, libjgb), Int32,
+        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
+    copyto!(a.deviceMagnitude, a.voltage.magnitude)
+    copyto!(a.deviceAngle, a.voltage.angle)
+    return nothing
+end
+"analysis.voltage is plain Julia data the user may edit or reset between calls: push it whenever it left the device copy"
+syncState!(a::AcPowerFlowB200) =
+    (a.voltage.magnitude == a.deviceMagnitude && a.voltage.angle == a.deviceAngle) || pushState!(a)
+
+"setInitialPoint!(analysis) (acPowerFlow.jl:1226-1249): the reference resets the shared voltage vectors; push them"
+function setInitialPoint!(a::AcPowerFlowB200)
+    setInitialPoint!(a.reference)
+    a.method.iteration = 0
+    pushState!(a)
+    return nothing
+end
+
+"power! (postprocessing/acAnalysis.jl:30-79) is a method of the reference's AcPowerFlow; the B200 analysis shares its
+voltage / power / current containers with that object, so the call is forwarded. current! (:672-700) is generic on `AC`
+and works on the B200 analysis as it is."
+power!(a::AcPowerFlowB200) = power!(a.reference)
 
 function mismatch!(a::AcPowerFlowB200)
+    syncState!(a)
     sp, sq = Ref{Float64}(0), Ref{Float64}(0)
     check(a.method.ctx, ccall((:jgb_nr_mismatch, libjgb), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}),
         a.method.ctx.handle, sp, sq))
@@ -95,6 +127,7 @@ function mismatch!(a::AcPowerFlowB200)
 end
 
 function solve!(a::AcPowerFlowB200)
+    syncState!(a)
     check(a.method.ctx, ccall((:jgb_nr_solve, libjgb), Int32, (Ptr{Cvoid},), a.method.ctx.handle))
     a.method.iteration += 1
     pullState!(a)
@@ -110,8 +143,8 @@ function powerFlow!(a::AcPowerFlowB200; iteration::Int64 = 20, tolerance::Float6
         a.method.ctx.handle, iteration, tolerance, it, sp, sq))
     a.method.iteration = it[]
     pullState!(a)
-    power && JuliaGrid.power!(a)        # generic `AC` post-processing of the reference keeps working
-    current && JuliaGrid.current!(a)
+    power && power!(a)
+    current && current!(a)
     return nothing
 end
 
@@ -135,6 +168,48 @@ mutable struct AcStateEstimationB200 <: AC
     method::GaussNewtonB200
     system::PowerSystem
     monitoring::Measurement
+    deviceMagnitude::Vector{Float64}
+    deviceAngle::Vector{Float64}
+    reference::Any                 # the reference's AcStateEstimation, built on the first power! call (post-processing only)
+end
+
+function pushState!(a::AcStateEstimationB200)
+    check(a.method.ctx, ccall((:jgb_wls_set_state, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+        a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
+    copyto!(a.deviceMagnitude, a.voltage.magnitude)
+    copyto!(a.deviceAngle, a.voltage.angle)
+    return nothing
+end
+function pullState!(a::AcStateEstimationB200)
+    check(a.method.ctx, ccall((:jgb_wls_get_state, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
+        a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
+    copyto!(a.deviceMagnitude, a.voltage.magnitude)
+    copyto!(a.deviceAngle, a.voltage.angle)
+    return nothing
+end
+syncState!(a::AcStateEstimationB200) =
+    (a.voltage.magnitude == a.deviceMagnitude && a.voltage.angle == a.deviceAngle) || pushState!(a)
+
+"setInitialPoint!(analysis) for state estimation (acStateEstimation.jl): back to the bus voltages of the system"
+function setInitialPoint!(a::AcStateEstimationB200)
+    copyto!(a.voltage.magnitude, a.system.bus.voltage.magnitude)
+    copyto!(a.voltage.angle, a.system.bus.voltage.angle)
+    a.method.iteration = 0
+    pushState!(a)
+    return nothing
+end
+
+# power! (postprocessing/acAnalysis.jl:221-262) is a method of the reference's AcStateEstimation: the reference object is
+# built once, on the first call, and only for this post-processing step; current! (:672-700) is generic on `AC`.
+function power!(a::AcStateEstimationB200)
+    if a.reference === nothing
+        a.reference = gaussNewton(a.monitoring)
+        a.power = a.reference.power
+    end
+    copyto!(a.reference.voltage.magnitude, a.voltage.magnitude)
+    copyto!(a.reference.voltage.angle, a.voltage.angle)
+    power!(a.reference)
+    return nothing
 end
 
 function gaussNewton(monitoring::Measurement, ::Type{B200}; device::Integer = 0)
@@ -157,13 +232,13 @@ function gaussNewton(monitoring::Measurement, ::Type{B200}; device::Integer = 0)
     check(ctx, ccall((:jgb_wls_set_mean, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}), ctx.handle, mean))
     m = GaussNewtonB200(mean, rsd, zeros(2 * bus.number), type, index, range, 0.0, 0, ctx)
     a = AcStateEstimationB200(Polar(copy(bus.voltage.magnitude), copy(bus.voltage.angle)), power, current, m,
-        system, monitoring)
-    check(ctx, ccall((:jgb_wls_set_state, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
-        ctx.handle, a.voltage.magnitude, a.voltage.angle))
+        system, monitoring, zeros(bus.number), zeros(bus.number), nothing)
+    pushState!(a)
     return a
 end
 
 function increment!(a::AcStateEstimationB200)
+    syncState!(a)
     mi, ob = Ref{Float64}(0), Ref{Float64}(0)
     check(a.method.ctx, ccall((:jgb_wls_increment, libjgb), Int32, (Ptr{Cvoid}, Ref{Float64}, Ref{Float64}),
         a.method.ctx.handle, mi, ob))
@@ -174,22 +249,21 @@ end
 function solve!(a::AcStateEstimationB200)
     check(a.method.ctx, ccall((:jgb_wls_solve, libjgb), Int32, (Ptr{Cvoid},), a.method.ctx.handle))
     a.method.iteration += 1
-    check(a.method.ctx, ccall((:jgb_wls_get_state, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
-        a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
+    pullState!(a)
     return nothing
 end
 
 function stateEstimation!(a::AcStateEstimationB200; iteration::Int64 = 40, tolerance::Float64 = 1e-8,
     power::Bool = false, current::Bool = false, verbose::Int64 = 0)
+    syncState!(a)
     it, mi, ob = Ref{Int64}(0), Ref{Float64}(0), Ref{Float64}(0)
     check(a.method.ctx, ccall((:jgb_wls_run, libjgb), Int32,
         (Ptr{Cvoid}, Int64, Float64, Ref{Int64}, Ref{Float64}, Ref{Float64}),
         a.method.ctx.handle, iteration, tolerance, it, mi, ob))
     a.method.iteration, a.method.objective = it[], ob[]
-    check(a.method.ctx, ccall((:jgb_wls_get_state, libjgb), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}),
-        a.method.ctx.handle, a.voltage.magnitude, a.voltage.angle))
-    power && JuliaGrid.power!(a)
-    current && JuliaGrid.current!(a)
+    pullState!(a)
+    power && power!(a)
+    current && current!(a)
     return nothing
 end
 

@@ -93,3 +93,40 @@ def ac_model(system: PowerSystem) -> AcModel:
     nzval_t = nzval[pos]
     return AcModel(n, (colptr + 1).astype(np.int64), (rowval + 1).astype(np.int64), nzval, nzval_t, adm,
                    y_ff, y_ft, y_tf, y_tt)
+
+
+def apply_branch_status(system: PowerSystem, k: int, status: int):
+    """Host side of updateBranch!(…; status) (updateBranchMain! powerSystem/branch.jl:313-431 + acNodalUpdate!
+    model.jl:81-110): the four Ybus entries of branch k change in place on the fixed pattern. Returns the 0-based nzval
+    positions touched, their new Y and Y-transpose values, and the branch's new series admittance."""
+    mdl = system.model
+    i, j = int(system.frm[k]), int(system.to[k])
+    pos = np.array([mdl.position(i, i), mdl.position(j, j), mdl.position(i, j), mdl.position(j, i)])
+    if status == int(system.status[k]):
+        return pos, mdl.nzval[pos].copy(), mdl.nzval_t[pos].copy(), mdl.admittance[k]
+    if status == 0:
+        dff, dft, dtf, dtt = -mdl.y_ff[k], -mdl.y_ft[k], -mdl.y_tf[k], -mdl.y_tt[k]
+    else:
+        one = system.copy()
+        one.status[:] = 0
+        one.status[k] = 1
+        one.model = None
+        tmp = ac_model(one)
+        dff, dft, dtf, dtt = tmp.y_ff[k], tmp.y_ft[k], tmp.y_tf[k], tmp.y_tt[k]
+        mdl.admittance[k] = tmp.admittance[k]
+    # nodalMatrix: (i,i)+=ff (j,j)+=tt (i,j)+=ft (j,i)+=tf ; transpose: the (j,i) position holds Y[i,j] etc.
+    mdl.nzval[pos[0]] += dff
+    mdl.nzval[pos[1]] += dtt
+    mdl.nzval[pos[2]] += dft
+    mdl.nzval[pos[3]] += dtf
+    mdl.nzval_t[pos[0]] += dff
+    mdl.nzval_t[pos[1]] += dtt
+    mdl.nzval_t[pos[3]] += dft
+    mdl.nzval_t[pos[2]] += dtf
+    if status == 0:
+        mdl.y_ff[k] = mdl.y_ft[k] = mdl.y_tf[k] = mdl.y_tt[k] = 0
+        mdl.admittance[k] = 0
+    else:
+        mdl.y_ff[k], mdl.y_ft[k], mdl.y_tf[k], mdl.y_tt[k] = dff, dft, dtf, dtt
+    system.status[k] = status
+    return pos, mdl.nzval[pos].copy(), mdl.nzval_t[pos].copy(), mdl.admittance[k]

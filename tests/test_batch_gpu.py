@@ -101,3 +101,27 @@ def test_batch_rejects_bad_arguments(ctx):
     lib = ctx.lib
     assert lib.jgb_nr_batch(ctx.handle, 0, None, None, None, 20, 1e-8, None, None, None, None, None) == -1
     assert lib.jgb_nr_run(ctx.handle, -1, 1e-8, None, None, None) == -1
+
+
+def test_task_kernel_matches_per_front_kernels(monkeypatch):
+    """JGB_TASKS=1 routes the small fronts of a batch through mf_task_kernel (subtrees per CTA, update blocks on a
+    shared-memory stack): same iterations and voltages as the default per-front kernels, ragged batch size included."""
+    ps = product_system("synthetic20")
+    elig = jgb200.eligible_outages(ps)[:70]
+    c0 = jgb200.Context(0)
+    ref = jgb200.nr_batch(jgb200.newton_raphson(ps, c0), elig)
+    monkeypatch.setenv("JGB_TASKS", "1")
+    for env in ({}, {"JGB_TASK_MAXNF": "8"}, {"JGB_TASK_STACK": "40", "JGB_TASK_BUNDLE": "5"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        c1 = jgb200.Context(0)
+        a = jgb200.newton_raphson(product_system("synthetic20"), c1)
+        res = jgb200.nr_batch(a, elig)
+        assert c1.stat("nr.batch.task_fronts") > 0
+        assert (res.status == 0).all() and np.array_equal(res.iterations, ref.iterations)
+        np.testing.assert_allclose(res.vm, ref.vm, atol=1e-12, rtol=0)
+        np.testing.assert_allclose(res.va, ref.va, atol=1e-12, rtol=0)
+        c1.close()
+        for k in env:
+            monkeypatch.delenv(k)
+    c0.close()

@@ -106,3 +106,25 @@ def test_bad_arguments_and_iteration_cap(ctx):
     assert not jgb200.power_flow_fnr(a, iteration=3) and a.method.iteration == 3
     assert jgb200.power_flow_fnr(a, iteration=100)
     fresh.close()
+
+
+def test_diverged_scenario_is_never_reported_converged(ctx):
+    """NaN / Inf injections make every mismatch of a scenario NaN: CUDA's fmax() drops NaN operands, so without the
+    NaN -> Inf mapping in fnr_mismatch_kernel the stop values would read 0 and the scenario would pass as converged."""
+    ps = product_system("case30test")
+    a = _make(ps, False, ctx)
+    sp, sq, _ = ps.supply
+    p = np.tile(sp - ps.pd, (3, 1))
+    q = np.tile(sq - ps.qd, (3, 1))
+    p[1, :] = np.nan
+    q[1, :] = np.nan
+    vm, va, it, st = jgb200.fnr_batch(a, p, q, iteration=50)
+    assert st[1] != 0
+    assert st[0] == 0 and st[2] == 0
+    assert np.isfinite(vm[0]).all() and np.isfinite(vm[2]).all()
+    assert np.abs(vm[0] - vm[2]).max() == 0.0
+    # oversized batches are refused before any launch
+    import ctypes as C
+    d = np.zeros(1)
+    dp = d.ctypes.data_as(C.POINTER(C.c_double))
+    assert ctx.lib.jgb_fnr_batch(ctx.handle, 65535 * 32 + 1, dp, dp, 10, 1e-8, dp, dp, None, None, None) == -1

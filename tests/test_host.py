@@ -267,3 +267,61 @@ def test_reactive_limit_host_logic_matches_oracle(case):
     np.testing.assert_allclose(sp_, os_.supply_p, rtol=0, atol=1e-12)
     np.testing.assert_allclose(sq_, os_.supply_q, rtol=0, atol=1e-12)
     np.testing.assert_allclose(ps.gen_q, os_.gen_q, rtol=0, atol=1e-12)
+
+
+def _build_c_driver(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "abi_c_test")
+    libdir = os.path.dirname(jgb200.LIB_PATH)
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "tests", "abi_c_test.c"), "-L", libdir, "-ljgb200", "-lm",
+                    f"-Wl,-rpath,{libdir}", "-o", exe], check=True)
+    return exe
+
+
+def test_plain_c_driver_links_every_header_symbol(tmp_path):
+    """tests/abi_c_test.c is compiled against include/jgb200.h and linked to the .so: a symbol declared but not exported
+    (or the reverse, through the table check below) fails here without ctypes in the loop."""
+    import subprocess
+    exe = _build_c_driver(tmp_path)
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    first = out.stdout.splitlines()[0].split()
+    assert first[0] == "symbols" and int(first[1]) == len(header_symbols())
+    src = open(os.path.join(ROOT, "tests", "abi_c_test.c")).read()
+    for name in header_symbols():
+        assert f"SYM({name})" in src, f"{name} is missing from the C driver's table"
+
+
+@pytest.mark.parametrize("case", ["case14test", "synthetic20", "synthetic10k", "case_ACTIVSg10k"])
+def test_task_partition_host_replay(case, monkeypatch):
+    """jgb_selfcheck_tasks: the task partition of the batch factorisation (fronts per CTA, shared-memory stack offsets,
+    per-warp entry lists) replayed on the host solves J x = f like the plain multifrontal replay, for several caps."""
+    o = onr.newton_raphson(oracle_system(case))
+    onr.mismatch(o)
+    onr.fill_jacobian(o)
+    n = o.dim
+    grp = np.zeros(n, dtype=np.int64)
+    for i in range(o.mdl.n):
+        if o.pvpq[i] >= 0:
+            grp[o.pvpq[i]] = i
+        if o.pq[i] >= 0:
+            grp[o.pq[i]] = i
+    cp, rv = (o.j_colptr + 1).astype(np.int64), (o.j_rowval + 1).astype(np.int64)
+    J = onr.jacobian_csc(o)
+    monkeypatch.setenv("JGB_TASKS", "1")
+    for env in ({}, {"JGB_TASK_MAXNF": "12", "JGB_TASK_STACK": "96"}, {"JGB_TASK_BUNDLE": "6", "JGB_TASK_META": "1500"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        x, st = np.zeros(n), np.zeros(8)
+        rc = jgb200.load().jgb_selfcheck_tasks(n, ptr(cp, C.c_int64), ptr(rv, C.c_int64), ptr(o.j_nzval, C.c_double),
+                                               ptr(grp, C.c_int64), ptr(o.mismatch, C.c_double), ptr(x, C.c_double),
+                                               ptr(st, C.c_double))
+        assert rc == 0
+        assert np.abs(J @ x - o.mismatch).max() <= 1e-10 * max(1.0, np.abs(o.mismatch).max())
+        # stats: launches, tasks, fronts in tasks, update elements kept on chip, smem bytes, blob ints, fronts, upd
+        assert st[0] >= 1 and st[2] >= 1 and st[4] <= 220 * 1024 and st[3] <= st[7]
+        if case.endswith("10k"):
+            assert st[2] > 0.8 * st[6] or env          # the default caps put most fronts into tasks
+        for k in env:
+            monkeypatch.delenv(k)
