@@ -30,13 +30,86 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
+class Refactor:
+    """KLU-style numeric refactorisation on a fixed pattern (oracle/csrc/oracle_lu.c): the first call factors with
+    SuperLU (ordering, pivot order, patterns of L and U); every later call reuses all of that and only recomputes the
+    values, like the reference's `lu!` / `klu!` after its first `factorization` (backend/utility.jl:470-500)."""
+
+    def __init__(self, lu_options=None):
+        self.lu_options = lu_options or {}
+        self.ready = False
+        self.symbolic_calls = 0
+        self.numeric_calls = 0
+
+    def _symbolic(self, J):
+        n = J.shape[0]
+        lu = spla.splu(J, **self.lu_options)                 # ordering + pivot order on the real values (klu_analyze + klu_factor)
+        # SciPy drops entries of L and U that are exactly zero in THIS factorisation (a flat start zeroes many Jacobian
+        # entries), so the structural patterns are taken from a second, pattern-only factorisation of Pr J Pc with
+        # generic values and a dominant diagonal: no pivoting can occur and nothing cancels.
+        row1 = np.asarray(lu.perm_r, dtype=np.int64)          # row i of J -> row perm_r[i]
+        col1 = np.asarray(lu.perm_c, dtype=np.int64)          # column j of J -> column perm_c[j]
+        coo = J.tocoo()
+        rng = np.random.default_rng(12345)
+        vals = 0.5 + rng.random(coo.nnz)
+        B = sp.csc_matrix((vals, (row1[coo.row], col1[coo.col])), shape=(n, n))
+        B = B + sp.diags(np.full(n, 4.0 * n)).tocsc()
+        lu2 = spla.splu(B.tocsc(), permc_spec="NATURAL", diag_pivot_thresh=0.0)
+        row2 = np.asarray(lu2.perm_r, dtype=np.int64)
+        col2 = np.asarray(lu2.perm_c, dtype=np.int64)
+        L, U = lu2.L.tocsc(), lu2.U.tocsc()
+        L.sort_indices()
+        U.sort_indices()
+        i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        self.n = n
+        self.Lp, self.Li, self.Lx = i32(L.indptr), i32(L.indices), np.zeros(L.nnz)
+        self.Up, self.Ui, self.Ux = i32(U.indptr), i32(U.indices), np.zeros(U.nnz)
+        # structural checks the C loops rely on: unit diagonal first in L, diagonal last in U
+        assert np.array_equal(self.Li[self.Lp[:-1]], np.arange(n)) and np.array_equal(self.Ui[self.Up[1:] - 1], np.arange(n))
+        self.row_new = i32(row2[row1])
+        col_src = np.empty(n, dtype=np.int32)
+        col_src[col2[col1]] = np.arange(n, dtype=np.int32)
+        self.col_src = col_src
+        self.work = np.zeros(n)
+        self.x = np.zeros(n)
+        self.ready = True
+        self.symbolic_calls += 1
+        self.nnz_lu = int(L.nnz + U.nnz - n)
+
+    def factor(self, J):
+        """J: csc_matrix with int32 indices on the pattern of the first call."""
+        first = not self.ready
+        if first:
+            self._symbolic(J)
+        rc = lib().olu_refactor(C.c_int32(self.n), _p(J.indptr, C.c_int32), _p(J.indices, C.c_int32),
+                                _p(J.data, C.c_double), _p(self.row_new, C.c_int32), _p(self.col_src, C.c_int32),
+                                _p(self.Lp, C.c_int32), _p(self.Li, C.c_int32), _p(self.Lx, C.c_double),
+                                _p(self.Up, C.c_int32), _p(self.Ui, C.c_int32), _p(self.Ux, C.c_double),
+                                _p(self.work, C.c_double))
+        self.numeric_calls += 0 if first else 1
+        if rc != 0:
+            raise np.linalg.LinAlgError(f"zero pivot in column {rc - 1} of the refactorisation")
+
+    def solve(self, b):
+        b = np.ascontiguousarray(b, dtype=np.float64)
+        lib().olu_solve(C.c_int32(self.n), _p(self.row_new, C.c_int32), _p(self.col_src, C.c_int32),
+                        _p(self.Lp, C.c_int32), _p(self.Li, C.c_int32), _p(self.Lx, C.c_double),
+                        _p(self.Up, C.c_int32), _p(self.Ui, C.c_int32), _p(self.Ux, C.c_double), _p(b, C.c_double),
+                        _p(self.x, C.c_double), _p(self.work, C.c_double))
+        return self.x.copy()
+
+
 class FastNR:
     """Newton-Raphson with the C assembly loops and SuperLU (`splu`) standing in for UMFPACK/KLU.
     lu_options=None -> SuperLU defaults (COLAMD + partial pivoting, closest to the reference's `LU`);
     NOPIVOT -> MMD_AT_PLUS_A, diag_pivot_thresh=0, SymmetricMode (the faster setting)."""
     NOPIVOT = dict(permc_spec="MMD_AT_PLUS_A", diag_pivot_thresh=0.0, options=dict(SymmetricMode=True))
 
-    def __init__(self, a: _nr.NewtonRaphson, lu_options=None):
+    def __init__(self, a: _nr.NewtonRaphson, lu_options=None, refactor=False):
+        # refactor=True: symbolic analysis + pivot order once (first solve of the object), numeric refactorisation
+        # afterwards — the reference's `factorization` / `factorization!` split; False: a fresh SuperLU call per solve
+        self.refactor = Refactor(lu_options) if refactor else None
+        self.t_asm = self.t_fac = self.t_sol = 0.0
         self.a = a
         m = a.mdl
         self.n = m.n
@@ -70,6 +143,13 @@ class FastNR:
         self.va[:] = self.va0
 
     def mismatch(self):
+        import time
+        t0 = time.perf_counter()
+        r = self._mismatch()
+        self.t_asm += time.perf_counter() - t0
+        return r
+
+    def _mismatch(self):
         L = lib()
         L.onr_mismatch(C.c_int64(self.n), _p(self.colptr, C.c_int64), _p(self.rowval, C.c_int64),
                        _p(self.yt, C.c_double), _p(self.type, C.c_int8), C.c_int64(self.a.slack),
@@ -88,9 +168,23 @@ class FastNR:
                        _p(self.va, C.c_double), _p(self.jnz, C.c_double))
 
     def solve(self):
+        import time
+        t0 = time.perf_counter()
         self.jacobian()
+        t1 = time.perf_counter()
         J = sp.csc_matrix((self.jnz, self.jrowval, self.jcolptr32), shape=(len(self.mism),) * 2)
-        inc = spla.splu(J, **self.lu_options).solve(self.mism)
+        if self.refactor is not None:
+            self.refactor.factor(J)
+            t2 = time.perf_counter()
+            inc = self.refactor.solve(self.mism)
+        else:
+            lu = spla.splu(J, **self.lu_options)
+            t2 = time.perf_counter()
+            inc = lu.solve(self.mism)
+        t3 = time.perf_counter()
+        self.t_asm += t1 - t0
+        self.t_fac += t2 - t1
+        self.t_sol += t3 - t2
         lib().onr_update(C.c_int64(self.n), _p(self.type, C.c_int8), C.c_int64(self.a.slack), _p(self.pq, C.c_int64),
                          _p(self.pvpq, C.c_int64), _p(np.ascontiguousarray(inc), C.c_double), _p(self.vm, C.c_double),
                          _p(self.va, C.c_double))
@@ -112,9 +206,11 @@ class FastWLS:
     """Gauss-Newton WLS with the C normalEquation! loops (codes 1, 6-11, 16, 17; diagonal precision), SciPy SpGEMM for
     H'WH like the reference's two stdlib SpGEMMs, and SuperLU with the symmetric no-pivot settings for the gain."""
 
-    def __init__(self, g, lu_options=None):
+    def __init__(self, g, lu_options=None, refactor=False):
         from . import wls as _w
         self.g = g
+        self.refactor = Refactor(lu_options or FastNR.NOPIVOT) if refactor else None
+        self.t_rows = self.t_gain = self.t_fac = self.t_sol = 0.0
         sysm, m = g.sys, g.mdl
         n = sysm.n
         self.n = n
@@ -167,6 +263,8 @@ class FastWLS:
         self.va[:] = self.va0
 
     def increment(self):
+        import time
+        t0 = time.perf_counter()
         L = lib()
         L.owls_normal_equation.restype = C.c_double
         P = lambda a, t=C.c_int64: _p(a, t)
@@ -183,10 +281,46 @@ class FastWLS:
         saved = self.hnz[lo:hi].copy()
         self.hnz[lo:hi] = 0.0
         H = sp.csc_matrix((self.hnz, self.hrow, self.hcolptr), shape=(self.g.m, 2 * n))
+        t1 = time.perf_counter()
         temp = (H.T @ self.W).tocsc()
-        gain = (temp @ H).tolil()
-        gain[sl, sl] = 1.0
-        inc = spla.splu(gain.tocsc(), **self.lu_options).solve(temp @ self.res)
+        gain = (temp @ H).tocsc()
+        gain.sort_indices()
+        # gain[slack, slack] = 1 (acStateEstimation.jl:889-891): the slack row / column of H is zero, the entry is stored
+        # (Julia keeps the explicit zero); SciPy drops it, so it is put back on a fixed pattern built once
+        if getattr(self, "_gpat", None) is None:
+            g0 = gain.tolil()
+            g0[sl, sl] = 1.0
+            g0 = g0.tocsc()
+            g0.sort_indices()
+            self._gpat = (g0.indptr.astype(np.int32), g0.indices.astype(np.int32))
+            self._gslack = int(g0.indptr[sl] + np.searchsorted(g0.indices[g0.indptr[sl]:g0.indptr[sl + 1]], sl))
+            self._gmap = None
+            if g0.nnz != gain.nnz:
+                keep = np.ones(g0.nnz, dtype=bool)
+                keep[self._gslack] = False
+                self._gmap = np.flatnonzero(keep)
+        data = np.zeros(len(self._gpat[1]))
+        if self._gmap is not None:
+            data[self._gmap] = gain.data
+        else:
+            data[:] = gain.data
+        data[self._gslack] = 1.0
+        G = sp.csc_matrix((data, self._gpat[1], self._gpat[0]), shape=gain.shape)
+        rhs = temp @ self.res
+        t2 = time.perf_counter()
+        if self.refactor is not None:
+            self.refactor.factor(G)
+            t3 = time.perf_counter()
+            inc = self.refactor.solve(rhs)
+        else:
+            lu = spla.splu(G, **self.lu_options)
+            t3 = time.perf_counter()
+            inc = lu.solve(rhs)
+        t4 = time.perf_counter()
+        self.t_rows += t1 - t0
+        self.t_gain += t2 - t1
+        self.t_fac += t3 - t2
+        self.t_sol += t4 - t3
         inc[sl] = 0.0
         self.hnz[lo:hi] = saved
         self.inc = inc

@@ -190,6 +190,7 @@ def test_c_wls_oracle_matches_numpy_oracle():
     g = owls.gauss_newton(os_, mon, o.mdl, lu_options=FastNR.NOPIVOT)
     g.mean += 1e-3 * np.random.default_rng(3).standard_normal(g.m)
     fw = FastWLS(g)
+    fr = FastWLS(g, refactor=True)
     assert fw.increment() == pytest.approx(owls.increment(g), rel=1e-12)
     assert np.array_equal(fw.res, g.residual) and np.array_equal(fw.hnz, g.h_nzval)
     assert fw.objective == pytest.approx(g.objective, rel=1e-13)
@@ -197,6 +198,49 @@ def test_c_wls_oracle_matches_numpy_oracle():
     assert fw.state_estimation() and owls.state_estimation(g)
     assert fw.iteration == g.iteration
     np.testing.assert_allclose(fw.vm, g.vm, atol=1e-12)
+    # the refactorisation arm (symbolic once, numeric refactor afterwards, like ldlt! / lu!) gives the same run
+    assert fr.state_estimation() and fr.iteration == g.iteration
+    assert fr.refactor.symbolic_calls == 1 and fr.refactor.numeric_calls == fr.iteration
+    np.testing.assert_allclose(fr.vm, g.vm, atol=1e-12)
+    np.testing.assert_allclose(fr.va, g.va, atol=1e-12)
+
+
+@pytest.mark.parametrize("case", ["case14test", "case30test", "synthetic20", "case_ACTIVSg10k"])
+@pytest.mark.parametrize("opts", [None, "nopivot"])
+def test_refactor_arm_matches_superlu(case, opts):
+    """oracle/csrc/oracle_lu.c: the KLU-style numeric refactorisation (pattern, ordering and pivot order of the first
+    factorisation reused) solves every later Newton system like a fresh SuperLU factorisation, for the default
+    (COLAMD + partial pivoting) and the no-pivot settings; the power flows take the same iterations."""
+    from oracle.fast import FastNR, Refactor
+    lu_opts = FastNR.NOPIVOT if opts else None
+    a = onr.newton_raphson(oracle_system(case))
+    f = FastNR(a, lu_opts)
+    r = Refactor(lu_opts)
+    rng = np.random.default_rng(0)
+    for it in range(3):
+        f.mismatch()
+        f.jacobian()
+        J = sp.csc_matrix((f.jnz, f.jrowval, f.jcolptr32), shape=(len(f.mism),) * 2)
+        r.factor(J)
+        x = r.solve(f.mism)
+        ref = spla.splu(J, **(lu_opts or {})).solve(f.mism)
+        scale = max(1.0, np.abs(ref).max())
+        # a frozen pivot order is less stable than fresh partial pivoting (klu_refactor has the same property): the big
+        # case, perturbed far from its operating point, is held to 1e-7 relative residual, the small ones to 1e-9
+        tol = 1e-7 if case == "case_ACTIVSg10k" else 1e-9
+        assert np.abs(J @ x - f.mism).max() <= tol * max(1.0, np.abs(f.mism).max())
+        np.testing.assert_allclose(x, ref, atol=10 * tol * scale, rtol=1e-5)
+        f.vm += 1e-3 * rng.standard_normal(f.n)          # new values on the same pattern
+        f.va += 1e-3 * rng.standard_normal(f.n)
+    assert r.symbolic_calls == 1 and r.numeric_calls == 2
+    if case != "case_ACTIVSg10k":
+        g0, g1 = FastNR(a, lu_opts), FastNR(a, lu_opts, refactor=True)
+        assert g0.power_flow() and g1.power_flow() and g0.iteration == g1.iteration
+        np.testing.assert_allclose(g0.vm, g1.vm, atol=1e-12)
+    # a singular matrix is reported, not silently factored
+    Z = sp.csc_matrix((np.zeros_like(f.jnz), f.jrowval, f.jcolptr32), shape=J.shape)
+    with pytest.raises(np.linalg.LinAlgError):
+        r.factor(Z)
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/docs/src/examples/cases/hdf5/case_ACTIVSg10k.h5"),
