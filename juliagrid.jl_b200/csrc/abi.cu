@@ -555,6 +555,8 @@ double jgb_stat(jgb_ctx* ctx, const char* key) {
 #endif
             return t;
         }
+        if (k == "comm.calls") return ctx->comm ? (double)ctx->comm->calls : 0.0;
+        if (k == "comm.nranks") return ctx->comm ? (double)ctx->comm->nranks : 0.0;
         if (k.rfind("nr.", 0) == 0 && ctx->nr) return ctx->nr->stat(k);
 #ifdef JGB_WITH_WLS
         if (k.rfind("wls.", 0) == 0 && ctx->wls) return ctx->wls->stat(k);

@@ -947,7 +947,22 @@ int WlsContext::batch(int64_t Sreal64, const double* Z, bool dev_in, int64_t max
 }
 
 double WlsContext::stat(const std::string& key) {
+    if (key.rfind("wls.batch.", 0) == 0) {
+        const Symbolic& b = solver_batch.sym;
+        if (key == "wls.batch.u_size") return (double)b.u_size;
+        if (key == "wls.batch.upd_size") return (double)b.upd_size;
+        if (key == "wls.batch.nnz_lu") return (double)b.nnz_lu;
+        if (key == "wls.batch.fronts") return b.nfronts;
+        if (key == "wls.batch.levels") return b.nlevels;
+        if (key == "wls.batch.flops") return b.flops;
+        if (key == "wls.batch.max_front") return b.max_front;
+        if (key == "wls.batch.launches_per_solve") return solver_batch.launches_per_solve(32);
+        return -1.0;
+    }
     const Symbolic& s = solver.sym;
+    if (key == "wls.time.rows_count") return (double)timer.count[kPhRows];
+    if (key == "wls.n") return n;
+    if (key == "wls.nbr") return nbr;
     if (key == "wls.time.rows_ms") return timer.ms[kPhRows];
     if (key == "wls.time.gain_ms") return timer.ms[kPhGain];
     if (key == "wls.time.factor_ms") return timer.ms[kPhFactor];

@@ -60,3 +60,69 @@ void olu_solve(int32_t n, const int32_t* row_new, const int32_t* col_src, const 
     }
     for (int32_t j = 0; j < n; ++j) x[col_src[j]] = work[j];
 }
+
+/* Structural patterns of L and U for B = L U without pivoting (B given by its CSC pattern, ascending rows): column j of
+ * L + U is the reach of B(:, j) in the graph of the columns of L already found (Gilbert & Peierls, SIAM J. Sci. Stat.
+ * Comput. 9, 1988 — the symbolic step KLU runs inside its first factorisation). Rows above the diagonal are visited in
+ * ascending order through a binary heap, which is a topological order and leaves U(:, j) sorted; L(:, j) is sorted at
+ * the end of the column. mark (n ints) and heap (n ints) are workspaces. Returns 0, or -1 when capL / capU is too small. */
+#include <stdlib.h>
+
+static int cmp_i32(const void* a, const void* b) {
+    const int32_t x = *(const int32_t*)a, y = *(const int32_t*)b;
+    return (x > y) - (x < y);
+}
+
+int olu_symbolic(int32_t n, const int32_t* Bp, const int32_t* Bi, int32_t* Lp, int32_t* Li, int64_t capL, int32_t* Up,
+                 int32_t* Ui, int64_t capU, int32_t* mark, int32_t* heap) {
+    int64_t nl = 0, nu = 0;
+    for (int32_t i = 0; i < n; ++i) mark[i] = -1;
+    for (int32_t j = 0; j < n; ++j) {
+        int32_t hn = 0;
+        Lp[j] = (int32_t)nl;
+        Up[j] = (int32_t)nu;
+        if (nl + 1 > capL) return -1;
+        Li[nl++] = j;                                  /* unit diagonal first */
+        mark[j] = j;
+#define OLU_VISIT(r)                                                         \
+    do {                                                                     \
+        const int32_t r_ = (r);                                              \
+        if (mark[r_] != j) {                                                 \
+            mark[r_] = j;                                                    \
+            if (r_ < j) {                                                    \
+                int32_t c = hn++;                                            \
+                while (c > 0 && heap[(c - 1) / 2] > r_) { heap[c] = heap[(c - 1) / 2]; c = (c - 1) / 2; } \
+                heap[c] = r_;                                                \
+            } else {                                                         \
+                if (nl + 1 > capL) return -1;                                \
+                Li[nl++] = r_;                                               \
+            }                                                                \
+        }                                                                    \
+    } while (0)
+        for (int32_t p = Bp[j]; p < Bp[j + 1]; ++p) OLU_VISIT(Bi[p]);
+        while (hn > 0) {
+            const int32_t k = heap[0];
+            const int32_t last = heap[--hn];           /* pop the minimum */
+            int32_t c = 0;
+            for (;;) {
+                int32_t ch = 2 * c + 1;
+                if (ch >= hn) break;
+                if (ch + 1 < hn && heap[ch + 1] < heap[ch]) ++ch;
+                if (heap[ch] >= last) break;
+                heap[c] = heap[ch];
+                c = ch;
+            }
+            if (hn > 0) heap[c] = last;
+            if (nu + 1 > capU) return -1;
+            Ui[nu++] = k;
+            for (int32_t q = Lp[k] + 1; q < Lp[k + 1]; ++q) OLU_VISIT(Li[q]);
+        }
+#undef OLU_VISIT
+        if (nu + 1 > capU) return -1;
+        Ui[nu++] = j;                                  /* diagonal last */
+        qsort(Li + Lp[j] + 1, (size_t)(nl - Lp[j] - 1), sizeof(int32_t), cmp_i32);
+    }
+    Lp[n] = (int32_t)nl;
+    Up[n] = (int32_t)nu;
+    return 0;
+}

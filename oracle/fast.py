@@ -44,28 +44,31 @@ class Refactor:
     def _symbolic(self, J):
         n = J.shape[0]
         lu = spla.splu(J, **self.lu_options)                 # ordering + pivot order on the real values (klu_analyze + klu_factor)
-        # SciPy drops entries of L and U that are exactly zero in THIS factorisation (a flat start zeroes many Jacobian
-        # entries), so the structural patterns are taken from a second, pattern-only factorisation of Pr J Pc with
-        # generic values and a dominant diagonal: no pivoting can occur and nothing cancels.
+        # SciPy drops the entries of L and U that are exactly zero in THIS factorisation (a flat start zeroes many
+        # Jacobian entries), so the structural patterns of Pr J Pc = L U are computed symbolically (olu_symbolic) for the
+        # ordering and pivot order SuperLU chose.
         row1 = np.asarray(lu.perm_r, dtype=np.int64)          # row i of J -> row perm_r[i]
         col1 = np.asarray(lu.perm_c, dtype=np.int64)          # column j of J -> column perm_c[j]
         coo = J.tocoo()
-        rng = np.random.default_rng(12345)
-        vals = 0.5 + rng.random(coo.nnz)
-        B = sp.csc_matrix((vals, (row1[coo.row], col1[coo.col])), shape=(n, n))
-        B = B + sp.diags(np.full(n, 4.0 * n)).tocsc()
-        lu2 = spla.splu(B.tocsc(), permc_spec="NATURAL", diag_pivot_thresh=0.0)
-        row2 = np.asarray(lu2.perm_r, dtype=np.int64)
-        col2 = np.asarray(lu2.perm_c, dtype=np.int64)
-        L, U = lu2.L.tocsc(), lu2.U.tocsc()
-        L.sort_indices()
-        U.sort_indices()
+        B = sp.csc_matrix((np.ones(coo.nnz), (row1[coo.row], col1[coo.col])), shape=(n, n))
+        B.sort_indices()
         i32 = lambda a: np.ascontiguousarray(a, dtype=np.int32)
+        Bp, Bi = i32(B.indptr), i32(B.indices)
+        cap = int(1.5 * (lu.L.nnz + lu.U.nnz)) + 4 * n
+        while True:
+            Lp, Up = np.zeros(n + 1, dtype=np.int32), np.zeros(n + 1, dtype=np.int32)
+            Li, Ui = np.zeros(cap, dtype=np.int32), np.zeros(cap, dtype=np.int32)
+            mark, heap = np.zeros(n, dtype=np.int32), np.zeros(n, dtype=np.int32)
+            rc = lib().olu_symbolic(C.c_int32(n), _p(Bp, C.c_int32), _p(Bi, C.c_int32), _p(Lp, C.c_int32),
+                                    _p(Li, C.c_int32), C.c_int64(cap), _p(Up, C.c_int32), _p(Ui, C.c_int32),
+                                    C.c_int64(cap), _p(mark, C.c_int32), _p(heap, C.c_int32))
+            if rc == 0:
+                break
+            cap *= 2
         self.n = n
-        self.Lp, self.Li, self.Lx = i32(L.indptr), i32(L.indices), np.zeros(L.nnz)
-        self.Up, self.Ui, self.Ux = i32(U.indptr), i32(U.indices), np.zeros(U.nnz)
-        # structural checks the C loops rely on: unit diagonal first in L, diagonal last in U
-        assert np.array_equal(self.Li[self.Lp[:-1]], np.arange(n)) and np.array_equal(self.Ui[self.Up[1:] - 1], np.arange(n))
+        self.Lp, self.Li, self.Lx = Lp, np.ascontiguousarray(Li[:Lp[n]]), np.zeros(int(Lp[n]))
+        self.Up, self.Ui, self.Ux = Up, np.ascontiguousarray(Ui[:Up[n]]), np.zeros(int(Up[n]))
+        row2 = col2 = np.arange(n)
         self.row_new = i32(row2[row1])
         col_src = np.empty(n, dtype=np.int32)
         col_src[col2[col1]] = np.arange(n, dtype=np.int32)
@@ -74,7 +77,7 @@ class Refactor:
         self.x = np.zeros(n)
         self.ready = True
         self.symbolic_calls += 1
-        self.nnz_lu = int(L.nnz + U.nnz - n)
+        self.nnz_lu = int(Lp[n] + Up[n] - n)
 
     def factor(self, J):
         """J: csc_matrix with int32 indices on the pattern of the first call."""
