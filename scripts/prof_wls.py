@@ -14,3 +14,12 @@ jgb200.add_pmu(mon, pw, a.voltage.magnitude, a.voltage.angle, buses=buses, polar
 se = jgb200.gauss_newton(mon, ctx)
 print("increment", jgb200.increment(se))
 print("increment", jgb200.increment(se))
+if len(sys.argv) > 2 and sys.argv[1] == "batch":
+    # Monte-Carlo batch of S draws, iteration cap 1 (two increments): launch list of the batch kernels
+    S = int(sys.argv[2])
+    t = se.method.tables
+    wd = np.array([t.w_nzval[t.w_colptr[c] - 1] for c in range(t.m)])
+    Z = np.stack([t.mean + np.sqrt(1 / wd) * np.random.default_rng(1000 + s).standard_normal(t.m) for s in range(S)])
+    jgb200.set_voltage_se(se, ps.vm, ps.va)
+    res = jgb200.wls_batch(se, Z, iteration=1)
+    print("batch", S, res.total_iterations)

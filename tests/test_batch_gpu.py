@@ -85,6 +85,22 @@ def test_activsg10k_contingency_batch(ctx):
     res = jgb200.nr_batch(a, ks)
     ok = res.status == 0
     assert ok.mean() > 0.9            # a few outages of this stressed case do not converge within 20 iterations
+    # ... and they are the SAME outages that fail under the oracle with a fresh partial-pivoting SuperLU factorisation
+    # per iteration: a no-pivot artefact of the device factorisation would show up as a disagreement here
+    from oracle.fast import FastNR
+    from oracle.model import apply_outage
+    os_ = oracle_system("case_ACTIVSg10k")
+    base = oracle.ac_model(os_)
+    f = FastNR(onr.newton_raphson(os_, base))
+    for pos, kk in enumerate(ks):
+        mo = apply_outage(os_, base, int(kk))
+        f.set_y(mo.nzval, mo.nzval_t)
+        f.reset()
+        conv = f.power_flow(20, 1e-8)
+        assert conv == bool(ok[pos]), f"outage {kk}: device status {res.status[pos]}, oracle converged {conv}"
+        if conv:
+            assert f.iteration == res.iterations[pos]
+            assert np.abs(f.vm - res.vm[pos]).max() < 1e-8 and np.abs(f.va - res.va[pos]).max() < 1e-8
     k = int(ks[np.flatnonzero(ok)[3]])
     jgb200.update_branch(a, k, 0)
     jgb200.set_initial_point(a)

@@ -111,6 +111,17 @@ def test_70k_bus_case_single_and_outage_batch(ctx):
         f.va[:] = res.va[pos]
         dp, dq = f.mismatch()
         assert dp < 1e-8 and dq < 1e-8
+    # every outage the device reports as not converged also fails under the oracle (fresh partial-pivoting SuperLU per
+    # iteration), and two of the converged ones take the same number of iterations there
+    for pos in list(np.flatnonzero(~ok)) + list(np.flatnonzero(ok)[[5, 40]]):
+        mo = apply_outage(os_, base, int(ks[pos]))
+        f.set_y(mo.nzval, mo.nzval_t)
+        f.reset()
+        conv = f.power_flow(20, 1e-8)
+        assert conv == bool(ok[pos]), f"outage {ks[pos]}: device status {res.status[pos]}, oracle converged {conv}"
+        if conv:
+            assert f.iteration == res.iterations[pos]
+            assert np.abs(f.vm - res.vm[pos]).max() < 1e-8
 
 
 def test_70k_bus_state_estimation_recovers_power_flow(ctx):
