@@ -304,6 +304,74 @@ __global__ void nr_power_kernel(NrDev d, int nbr, const int* __restrict__ bf, co
     }
 }
 
+// ---- pivot guard: residual r = f - J * inc of the flagged scenarios (rare path: atomics are fine) -------------------------
+__global__ void nr_weak_count_kernel(const int* __restrict__ weak, const unsigned char* __restrict__ active, int S,
+                                     unsigned char* __restrict__ mask, int* __restrict__ counter) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const bool w = weak[s] != 0 && (!active || active[s]);
+    mask[s] = w ? 1 : 0;
+    if (w) atomicAdd(counter, 1);
+}
+
+__global__ void nr_refine_copy_kernel(const double* __restrict__ f, double* __restrict__ r,
+                                      const unsigned char* __restrict__ mask, int dim, int S) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)dim * S) return;
+    if (mask[gid % S]) r[gid] = f[gid];
+}
+
+__global__ void nr_refine_residual_kernel(const int* __restrict__ jcolptr, const int* __restrict__ jrow,
+                                          const double* __restrict__ jval, const double* __restrict__ inc,
+                                          double* __restrict__ r, const unsigned char* __restrict__ mask, int dim, int S) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)dim * S) return;
+    const int c = (int)(gid / S), s = (int)(gid % S);
+    if (!mask[s]) return;
+    const double x = inc[gid];
+    for (int q = jcolptr[c]; q < jcolptr[c + 1]; ++q)
+        atomicAdd(&r[(long long)jrow[q] * S + s], -jval[(long long)q * S + s] * x);
+}
+
+__global__ void nr_refine_add_kernel(double* __restrict__ inc, const double* __restrict__ inc2,
+                                     const unsigned char* __restrict__ mask, int dim, int S) {
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (long long)dim * S) return;
+    if (mask[gid % S]) inc[gid] += inc2[gid];
+}
+
+}  // namespace
+
+int NrContext::refine_weak(MfSolver& sol, int S, double* jval, double* f, double* inc, const unsigned char* active,
+                           int* status, int* weak) {
+    d_weakcnt.alloc(1);
+    r_mask.alloc(S);
+    JGB_CUDA(cudaMemsetAsync(d_weakcnt.p, 0, sizeof(int), stream));
+    nr_weak_count_kernel<<<ceil_div(S, 128), 128, 0, stream>>>(weak, active, S, r_mask.p, d_weakcnt.p);
+    ++launches;
+    JGB_CUDA(cudaMemcpyAsync(h_int.p + 2, d_weakcnt.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    JGB_CUDA(cudaStreamSynchronize(stream));
+    const int cnt = h_int.p[2];
+    if (cnt == 0) return 0;
+    weak_events += cnt;
+    ++refine_calls;
+    const long long ds = (long long)dim * S;
+    r_res.alloc((size_t)ds);
+    r_inc.alloc((size_t)ds);
+    const int blocks = (int)((ds + 255) / 256);
+    nr_refine_copy_kernel<<<blocks, 256, 0, stream>>>(f, r_res.p, r_mask.p, dim, S);
+    nr_refine_residual_kernel<<<blocks, 256, 0, stream>>>(d_jcolptr.p, d_jrow.p, jval, inc, r_res.p, r_mask.p, dim, S);
+    // the same factorisation again, carrying the residual as right-hand side (L is never stored), flagged scenarios only
+    sol.set_pivot_guard(nullptr, 1e300);
+    sol.factor_solve(jval, r_res.p, r_inc.p, S, r_mask.p, status, stream);
+    sol.set_pivot_guard(weak, pivot_growth);
+    nr_refine_add_kernel<<<blocks, 256, 0, stream>>>(inc, r_inc.p, r_mask.p, dim, S);
+    launches += 3 + sol.launches_per_solve(S);
+    JGB_CUDA(cudaGetLastError());
+    return cnt;
+}
+
+namespace {
 }  // namespace
 
 void NrContext::set_branches(int64_t nbr_, const int64_t* from, const int64_t* to, const double* yff, const double* yft,
@@ -444,6 +512,9 @@ void NrContext::setup(int64_t n_, const int64_t* ycp, const int64_t* yrv, const 
     d_pvpq.upload(pvpq, stream);
     d_pcount.upload(pcount, stream);
     d_jcolptr.upload(jcp, stream);
+    d_jrow.upload(jrv, stream);
+    d_weak.alloc(1);
+    d_weak.zero(stream);
     d_sup_p.alloc(n); d_sup_q.alloc(n); d_dem_p.alloc(n); d_dem_q.alloc(n);
     d_vm.alloc(n); d_va.alloc(n); d_f.alloc(dim); d_jval.alloc(nnzj); d_inc.alloc(dim);
     d_stop.alloc(2); d_stopbits.alloc(2); d_active.alloc(1); d_status.alloc(1); d_iters.alloc(1);
@@ -566,8 +637,11 @@ void NrContext::solve() {
         ++launches;
     }
     JGB_CUDA(cudaMemsetAsync(d_status.p, 0, sizeof(int), stream));
+    JGB_CUDA(cudaMemsetAsync(d_weak.p, 0, sizeof(int), stream));
+    solver.set_pivot_guard(d_weak.p, pivot_growth);
     solver.factor_solve(d_jval.p, d_f.p, d_inc.p, 1, nullptr, d_status.p, stream);
     launches += solver.launches_per_solve(1);
+    refine_weak(solver, 1, d_jval.p, d_f.p, d_inc.p, nullptr, d_status.p, d_weak.p);
     nr_update_kernel<<<ceil_div(n, 128), 128, 0, stream>>>(d, 1);
     ++launches;
     JGB_CUDA(cudaMemcpyAsync(h_int.p, d_status.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
@@ -596,6 +670,9 @@ int NrContext::run(int64_t max_iter, double tol, int64_t* iters, double* sp, dou
     JGB_CUDA(cudaMemcpyAsync(d_status.p, &one, sizeof(int), cudaMemcpyHostToDevice, stream));
     iteration = 0;
     int rc = 1;
+    // the graph loop only records weak pivots (nr.weak_pivot_scenarios); the refinement step runs in solve() and in batches
+    JGB_CUDA(cudaMemsetAsync(d_weak.p, 0, sizeof(int), stream));
+    solver.set_pivot_guard(d_weak.p, pivot_growth);
     const int per_solve = solver.launches_per_solve(1);      // also plans / allocates before any capture
     // mismatch! + convergence bookkeeping + the 16-byte read-back: the head of every loop trip
     auto enqueue_head = [&] {
@@ -643,6 +720,9 @@ int NrContext::run(int64_t max_iter, double tol, int64_t* iters, double* sp, dou
         iteration += 1;
     }
     JGB_CUDA(cudaGetLastError());
+    JGB_CUDA(cudaMemcpyAsync(h_int.p + 2, d_weak.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+    JGB_CUDA(cudaStreamSynchronize(stream));
+    if (h_int.p[2]) ++weak_events;
     jac_valid = true;
     if (iters) *iters = iteration;
     if (sp) *sp = h_stop.p[0];
@@ -656,7 +736,7 @@ void NrContext::alloc_state(int S) {
     b_vm.alloc((size_t)n * S); b_va.alloc((size_t)n * S); b_f.alloc((size_t)dim * S);
     b_jval.alloc((size_t)nnzj * S); b_inc.alloc((size_t)dim * S); b_stop.alloc(2 * (size_t)S);
     b_stopbits.alloc(2 * (size_t)S); b_active.alloc(S); b_status.alloc(S); b_iters.alloc(S);
-    b_of.alloc(S); b_ot.alloc(S); b_dy.alloc(4 * (size_t)S);
+    b_of.alloc(S); b_ot.alloc(S); b_dy.alloc(4 * (size_t)S); b_weak.alloc(S);
     batch_S = S;
 }
 
@@ -702,10 +782,13 @@ int NrContext::batch(int64_t Sreal64, const int64_t* of, const int64_t* ot, cons
         size_t f0 = timer.last();
         cudaEvent_t mid = timer.reserve();
         size_t f1 = timer.last();
+        JGB_CUDA(cudaMemsetAsync(b_weak.p, 0, (size_t)S * sizeof(int), stream));
+        solver_batch.set_pivot_guard(b_weak.p, pivot_growth);
         solver_batch.factor_solve(b_jval.p, b_f.p, b_inc.p, S, b_active.p, b_status.p, stream, mid);
         launches += solver_batch.launches_per_solve(S);
         timer.mark(stream);
         size_t f2 = timer.last();
+        refine_weak(solver_batch, S, b_jval.p, b_f.p, b_inc.p, b_active.p, b_status.p, b_weak.p);
         timer.span(kPhFactor, f0, f1);
         timer.span(kPhBacksolve, f1, f2);
         nr_update_kernel<<<(int)((ns + 127) / 128), 128, 0, stream>>>(d, S);
@@ -766,6 +849,8 @@ double NrContext::stat(const std::string& key) {
         return -1.0;
     }
     const Symbolic& s = solver.sym;
+    if (key == "nr.weak_pivot_scenarios") return (double)weak_events;
+    if (key == "nr.refine_calls") return (double)refine_calls;
     if (key == "nr.time.assemble_ms") return timer.ms[kPhAssemble];
     if (key == "nr.time.factor_ms") return timer.ms[kPhFactor];
     if (key == "nr.time.backsolve_ms") return timer.ms[kPhBacksolve];

@@ -69,6 +69,16 @@ class NrContext {
   private:
     void alloc_state(int S);
     void launch_assemble(int S, bool batch);
+    // Pivot guard + one step of iterative refinement (the factorisation has no pivoting; UMFPACK / KLU in the reference
+    // pivot by threshold): scenarios whose elimination met a multiplier above `pivot_growth` get delta += J^-1 (f - J delta)
+    // with the residual formed from the assembled Jacobian values. Returns the number of scenarios refined.
+    int refine_weak(MfSolver& sol, int S, double* jval, double* f, double* inc, const unsigned char* active, int* status,
+                    int* weak);
+    double pivot_growth = getenv("JGB_PIVOT_GROWTH") ? atof(getenv("JGB_PIVOT_GROWTH")) : 1e6;
+    long long weak_events = 0, refine_calls = 0;
+    DevBuf<int> d_jrow, d_weak, b_weak, d_weakcnt;
+    DevBuf<double> r_res, r_inc;
+    DevBuf<unsigned char> r_mask;
     NrDev view(int S, bool batch);
 
     cudaStream_t stream;

@@ -138,7 +138,7 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
             __syncthreads();
         }
     }
-    bool bad = false;
+    bool bad = false, weakp = false;
     const int colstride = nf * TS;
     // Blocked right-looking elimination, panels of B pivots:
     //  (a) panel: rank-1 steps restricted to the panel columns (one barrier each, a handful of multiply-adds per
@@ -170,6 +170,7 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
             for (int i = p + 1 + e0; i < nf; i += TE) {
                 double* rowi = pan + i * TS;
                 const double li = rowi[(p - p0) * colstride] * inv;
+                if (fabs(li) > sy.growth) weakp = true;
                 rowi[(p - p0) * colstride] = li;
                 for (int j = p + 1; j < pe; ++j) rowi[(j - p0) * colstride] -= li * pan[(p + (j - p0) * nf) * TS];
             }
@@ -267,6 +268,7 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
     }
     if (!act) return;
     if (bad && e0 == 0) status[s] = -3;
+    if (weakp && sy.weak) sy.weak[s] = 1;
     double* __restrict__ Uf = U + fd.uoff * S + s;
     for (int p = ec; p < k; p += TC) {
         double* Urow = Uf + urow_off(p, nf) * S;
@@ -602,7 +604,7 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
 #pragma unroll
         for (int i = 0; i < MAXNF; ++i) col[q][i] = (c <= nf && i < nf) ? Fl[(i + c * nf) * 32] : 0.0;
     }
-    bool bad = false;
+    bool bad = false, weakp = false;
     double* __restrict__ Uf = U + fd.uoff * S + s;
 #pragma unroll
     for (int p = 0; p < MAXNF; ++p) {
@@ -627,15 +629,18 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
             if (act && in) Urow[wide(c - p, S)] = (c == p) ? inv : upc;
             m[q] = (in && c > p) ? inv * upc : 0.0;
         }
+        const bool chk = e0 == p % TE;                  // one warp per pivot watches the multipliers
 #pragma unroll
         for (int i = p + 1; i < MAXNF; ++i) {
             const double li = (i < nf) ? b[i * 32] : 0.0;   // pivot-column entry, read once for all owned columns
+            if (chk && fabs(li * inv) > sy.growth) weakp = true;
 #pragma unroll
             for (int q = 0; q < NC; ++q) col[q][i] -= li * m[q];
         }
     }
     if (!act) return;
     if (bad && e0 == 0) status[s] = -3;
+    if (weakp && sy.weak) sy.weak[s] = 1;
     double* __restrict__ Cf = uptile + fd.updoff * 32 + sl;
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
@@ -1078,6 +1083,8 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
     set_task_smem_attr();
     dev.upd_size = sym.upd_size;
     dev.child_desc = d_child_desc.p;
+    dev.weak = nullptr;
+    dev.growth = 1e300;
     JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
 }
 

@@ -19,6 +19,10 @@ struct DevSym {
     const long long *f_uoff, *f_updoff;
     long long upd_size;
     const struct ChildDesc* child_desc;
+    // pivot guard (LU without pivoting): a multiplier |F[i,p] / F[p,p]| above `growth` marks the scenario in weak[] (nullable);
+    // the caller then refines the solution of that scenario with one residual step
+    int* weak;
+    double growth;
 };
 
 // Per-front descriptor, laid out in launch order (one 64-byte read replaces the fronts[] -> f_* double indirection)
@@ -80,6 +84,9 @@ class MfSolver {
     // major, rows / columns in f_rows order) at zoff_host[f].
     const double* selected_inverse(cudaStream_t st);
     std::vector<long long> zoff_host;
+    // Pivot guard: weak[s] (device, nullable) is set to 1 when a multiplier of scenario s exceeds `growth` during the
+    // next factor_solve calls (the partial pivoting of UMFPACK / KLU would have swapped rows there).
+    void set_pivot_guard(int* weak, double growth) { dev.weak = weak; dev.growth = growth; }
     int64_t factor_bytes(int S) const;     // algorithmic HBM bytes of one factor_solve (for roofline reports)
     int launches_per_solve(int S);
     int factor_launches(int S) { plan(S); return (int)(fplan.size() + tplan.size()); }

@@ -288,25 +288,22 @@ class FastWLS:
         temp = (H.T @ self.W).tocsc()
         gain = (temp @ H).tocsc()
         gain.sort_indices()
-        # gain[slack, slack] = 1 (acStateEstimation.jl:889-891): the slack row / column of H is zero, the entry is stored
-        # (Julia keeps the explicit zero); SciPy drops it, so it is put back on a fixed pattern built once
+        # gain[slack, slack] = 1 (acStateEstimation.jl:889-891). Julia's SpGEMM keeps the structural pattern of H'WH;
+        # SciPy's drops every entry whose sum happens to be zero, so its pattern moves with the values. The fixed
+        # pattern (|H|'|H| plus the slack diagonal) is built once and each iteration's values are placed into it.
+        nv = 2 * n
         if getattr(self, "_gpat", None) is None:
-            g0 = gain.tolil()
-            g0[sl, sl] = 1.0
-            g0 = g0.tocsc()
-            g0.sort_indices()
-            self._gpat = (g0.indptr.astype(np.int32), g0.indices.astype(np.int32))
-            self._gslack = int(g0.indptr[sl] + np.searchsorted(g0.indices[g0.indptr[sl]:g0.indptr[sl + 1]], sl))
-            self._gmap = None
-            if g0.nnz != gain.nnz:
-                keep = np.ones(g0.nnz, dtype=bool)
-                keep[self._gslack] = False
-                self._gmap = np.flatnonzero(keep)
-        data = np.zeros(len(self._gpat[1]))
-        if self._gmap is not None:
-            data[self._gmap] = gain.data
-        else:
-            data[:] = gain.data
+            Ho = sp.csc_matrix((np.ones(len(self.hrow)), self.hrow, self.hcolptr), shape=(self.g.m, nv))
+            P = (Ho.T @ Ho + sp.csc_matrix(([1.0], ([sl], [sl])), shape=(nv, nv))).tocsc()
+            P.sort_indices()
+            self._gpat = (P.indptr.astype(np.int32), P.indices.astype(np.int32))
+            cols = np.repeat(np.arange(nv, dtype=np.int64), np.diff(P.indptr))
+            self._gkeys = cols * nv + P.indices.astype(np.int64)
+            self._gslack = int(np.searchsorted(self._gkeys, sl * nv + sl))
+        gcols = np.repeat(np.arange(nv, dtype=np.int64), np.diff(gain.indptr))
+        pos = np.searchsorted(self._gkeys, gcols * nv + gain.indices.astype(np.int64))
+        data = np.zeros(len(self._gkeys))
+        data[pos] = gain.data
         data[self._gslack] = 1.0
         G = sp.csc_matrix((data, self._gpat[1], self._gpat[0]), shape=gain.shape)
         rhs = temp @ self.res

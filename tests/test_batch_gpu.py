@@ -141,3 +141,47 @@ def test_task_kernel_matches_per_front_kernels(monkeypatch):
         for k in env:
             monkeypatch.delenv(k)
     c0.close()
+
+
+def test_pivot_guard_refinement_path(monkeypatch):
+    """The factorisation has no pivoting; a multiplier above JGB_PIVOT_GROWTH (default 1e6) flags the scenario and its
+    increment gets one step of iterative refinement (residual from the assembled Jacobian, same factorisation again).
+    Power-flow Jacobians of the test grids never come near 1e6, so the threshold is lowered to 0.5 here: EVERY scenario
+    and every solve! takes the refinement path, and the results must still equal the oracle's — iteration for iteration."""
+    monkeypatch.setenv("JGB_PIVOT_GROWTH", "0.5")
+    c = jgb200.Context(0)
+    ps, os_ = product_system("case30test"), oracle_system("case30test")
+    a = jgb200.newton_raphson(ps, c)
+    elig = jgb200.eligible_outages(ps)[:36]
+    res = jgb200.nr_batch(a, elig)
+    assert (res.status == 0).all()
+    assert c.stat("nr.weak_pivot_scenarios") >= 36 and c.stat("nr.refine_calls") >= 1
+    for pos in (0, 17, 35):
+        o_sys = os_.copy()
+        o_sys.status[int(elig[pos])] = 0
+        o = onr.newton_raphson(o_sys)
+        assert onr.power_flow(o)
+        assert res.iterations[pos] == o.iteration
+        np.testing.assert_allclose(res.vm[pos], o.vm, atol=1e-8, rtol=0)
+        np.testing.assert_allclose(res.va[pos], o.va, atol=1e-8, rtol=0)
+    # stepwise operators: the refined increment solves J d = f to rounding
+    import scipy.sparse as sp
+    jgb200.set_initial_point(a)
+    jgb200.mismatch(a)
+    f = a.mismatch.copy()
+    jgb200.solve(a)
+    m = a.method
+    J = sp.csc_matrix((a.jacobian_nzval, m.jacobian_rowval - 1, m.jacobian_colptr - 1), shape=(len(f), len(f)))
+    assert np.abs(J @ a.increment - f).max() <= 1e-13 * max(1.0, np.abs(f).max())
+    calls = c.stat("nr.refine_calls")
+    assert calls >= 2
+    # with the default threshold nothing is flagged on this grid
+    monkeypatch.delenv("JGB_PIVOT_GROWTH")
+    c2 = jgb200.Context(0)
+    b = jgb200.newton_raphson(product_system("case30test"), c2)
+    res2 = jgb200.nr_batch(b, elig)
+    assert c2.stat("nr.weak_pivot_scenarios") == 0 and c2.stat("nr.refine_calls") == 0
+    assert np.array_equal(res2.iterations, res.iterations)
+    np.testing.assert_allclose(res2.vm, res.vm, atol=1e-12, rtol=0)
+    c.close()
+    c2.close()
