@@ -299,7 +299,7 @@ def run_reference(args):
     line = out.get("wls") if args.workload == "wls" else out["nr"]
     if args.workload == "all":
         line["wls"] = out["wls"]
-    print(json.dumps(line))
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------------- our arm
@@ -858,8 +858,29 @@ def run_ours(args):
                 line.update(other_extras(job, truth[0], a))
             except Exception as e:
                 line["extras_error"] = str(e)
-    print(json.dumps(line))
+    emit(line)
     job.close()
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+    """stdout carries the one JSON line and nothing else: file descriptor 1 is pointed at stderr for the whole run (NCCL,
+    the CUDA runtime and worker processes may print there), the line itself goes to a duplicate of the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -877,6 +898,7 @@ def main():
     ap.add_argument("--draws", type=int, default=1000,
                     help="Monte-Carlo draws per GPU per step (default: the 1000 draws of configs[4])")
     args = ap.parse_args()
+    protect_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

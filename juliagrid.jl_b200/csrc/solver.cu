@@ -297,21 +297,21 @@ __device__ __forceinline__ int sym_col(int j, int nf) { return (j * (2 * nf - j 
 
 template <int TS>
 __global__ void __launch_bounds__(TS == 1 ? 1024 : 256)
-mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ aval,
+mf_factor_sym_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const double* __restrict__ aval,
                      const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S, int TR,
                      const unsigned char* __restrict__ active, int* __restrict__ status) {
     extern __shared__ double Fs[];
     const int sl = threadIdx.x % TS;
     double* Fl = Fs + sl;
-    const int f = fronts[blockIdx.x];
+    const FrontDesc fd = descs[blockIdx.x];
     const int e0 = threadIdx.x / TS;
     const int TE = blockDim.x / TS;
     const int er = e0 % TR, ec = e0 / TR, TC = TE / TR;
     const int s = blockIdx.y * TS + sl;
     const bool act = active ? (active[s] != 0) : true;
     if (!__syncthreads_or(act)) return;
-    const int nf = sy.f_nf[f], k = sy.f_k[f], u = nf - k;
-    const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
+    const int nf = fd.nf, k = fd.k, u = nf - k;
+    const int* __restrict__ rows = sy.f_rows + fd.rowptr;
     const int tri = (nf * (nf + 1)) >> 1;
     double* Rl = Fl + tri * TS;                 // rhs: element i at Rl[i * TS]
     double* Lp = Fl + (tri + nf) * TS;          // panel multipliers: element (i, q) at Lp[(i + q*nf) * TS]
@@ -320,8 +320,8 @@ mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __
     __syncthreads();
     if (act) {
         const double* __restrict__ av = aval + s;
-        const int a1 = sy.f_asmptr[f + 1];
-        for (int a = sy.f_asmptr[f] + e0; a < a1; a += TE) {
+        const int a1 = fd.asm1;
+        for (int a = fd.asm0 + e0; a < a1; a += TE) {
             const int dst = sy.asm_dst[a];
             const int c = dst / nf, r = dst - c * nf;
             if (r >= c) Fl[(sym_col(c, nf) + r - c) * TS] = av[wide(sy.asm_src[a], S)];
@@ -331,21 +331,18 @@ mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __
     __syncthreads();
     const int W = S < 32 ? S : 32;
     double* __restrict__ up = upd + (long long)(s / W) * sy.upd_size * W + (s % W);
-    {
-        const int r1 = sy.f_eaptr[f + 1];
-        for (int rd = sy.f_eaptr[f]; rd < r1; ++rd) {
-            const int t1 = sy.ea_roundptr[rd + 1];
-            if (act) {
+    // gather of the children's blocks in rounds over the symmetric lists: lower triangle + rhs only, packed destinations
+    // (the rhs vector follows the triangle, so one index addresses both)
+    for (int rd = fd.ea0; rd < fd.ea1; ++rd) {
+        const int t1 = sy.ea_roundptr_s[rd + 1];
+        if (act) {
 #pragma unroll 4
-                for (int t = sy.ea_roundptr[rd] + e0; t < t1; t += TE) {
-                    const int2 pr = sy.ea_pair[t];
-                    const int c = pr.x / nf, r = pr.x - c * nf;
-                    if (c == nf) Rl[r * TS] += up[(unsigned)(pr.y * W)];
-                    else if (r >= c) Fl[(sym_col(c, nf) + r - c) * TS] += up[(unsigned)(pr.y * W)];
-                }
+            for (int t = sy.ea_roundptr_s[rd] + e0; t < t1; t += TE) {
+                const int2 pr = sy.ea_pair_s[t];
+                Fl[pr.x * TS] += up[(unsigned)(pr.y * W)];
             }
-            __syncthreads();
         }
+        __syncthreads();
     }
     bool bad = false;
     for (int p0 = 0; p0 < k; p0 += B) {
@@ -405,7 +402,7 @@ mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __
     }
     if (!act) return;
     if (bad && e0 == 0) status[s] = -3;
-    double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
+    double* __restrict__ Uf = U + fd.uoff * S + s;
     for (int p = ec; p < k; p += TC) {
         double* Urow = Uf + urow_off(p, nf) * S;
         const double* colp = Fl + (sym_col(p, nf) - p) * TS;
@@ -414,10 +411,11 @@ mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __
             Urow[wide(j - p, S)] = (j == p) ? 1.0 / v : v;
         }
     }
-    double* __restrict__ Cf = up + sy.f_updoff[f] * W;
+    double* __restrict__ Cf = up + fd.updoff * W;
+    const bool lower_only = fd.flags & 1;       // the parent is an LDL^T front too: it never reads above the diagonal
     for (int j = ec; j <= u; j += TC) {
         double* Cj = Cf + (unsigned)(j * u * W);
-        for (int i = er; i < u; i += TR) {
+        for (int i = (lower_only && j < u) ? j + ((er - j % TR + TR) % TR) : er; i < u; i += TR) {
             double v;
             if (j == u) v = Rl[(k + i) * TS];
             else {
@@ -429,8 +427,8 @@ mf_factor_sym_kernel(DevSym sy, const int* __restrict__ fronts, const double* __
     }
 }
 
-void launch_factor_sym(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st, DevSym dev, const int* fronts,
-                       const double* aval, const double* rhs, double* U, double* upd, int S, int tr,
+void launch_factor_sym(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st, DevSym dev,
+                       const FrontDesc* fronts, const double* aval, const double* rhs, double* U, double* upd, int S, int tr,
                        const unsigned char* active, int* status) {
 #define JGB_CASE(T)                                                                                                \
     case T:                                                                                                        \
@@ -655,6 +653,7 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
 }
 
 #include "mf_task.cuh"
+#include "mf_dense.cuh"
 
 template <bool GLOBAL_F>
 void launch_factor(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st, DevSym dev, const int* fronts,
@@ -1044,6 +1043,10 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
     d_f_eaptr.upload(sym.f_eaptr, st);
     d_ea_roundptr.upload(sym.ea_roundptr, st);
     d_ea_pair.upload(sym.ea_pair, st);
+    if (symmetric) {
+        d_ea_roundptr_s.upload(sym.ea_roundptr_sym, st);
+        d_ea_pair_s.upload(sym.ea_pair_sym, st);
+    }
     d_level_fronts.upload(sym.level_fronts, st);
     {
         std::vector<ChildDesc> cds(sym.f_children.size());
@@ -1067,6 +1070,8 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
     dev.asm_dst = d_asm_dst.p; dev.f_uoff = d_f_uoff.p; dev.f_updoff = d_f_updoff.p;
     dev.f_eaptr = d_f_eaptr.p; dev.ea_roundptr = d_ea_roundptr.p;
     dev.ea_pair = reinterpret_cast<const int2*>(d_ea_pair.p);
+    dev.ea_roundptr_s = d_ea_roundptr_s.p;
+    dev.ea_pair_s = reinterpret_cast<const int2*>(d_ea_pair_s.p);
     planned_S = -1;
     set_factor_smem_attr<1>(); set_factor_smem_attr<2>(); set_factor_smem_attr<4>();
     set_factor_smem_attr<8>(); set_factor_smem_attr<16>(); set_factor_smem_attr<32>();
@@ -1081,6 +1086,7 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
     JGB_BULK_VARIANTS(X)
 #undef X
     set_task_smem_attr();
+    JGB_CUDA(cudaFuncSetAttribute(mf_factor_dense_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     dev.upd_size = sym.upd_size;
     dev.child_desc = d_child_desc.p;
     dev.weak = nullptr;
@@ -1158,7 +1164,18 @@ void MfSolver::plan(int S) {
     const bool bulk_enabled = !(nb && *nb == '1');
     const std::vector<PlanRule> rules = (S == 1) ? parse_rules("JGB_FPLAN_SINGLE", symmetric ? single_rules_sym : single_rules)
                                                  : parse_rules("JGB_FPLAN_BATCH", symmetric ? batch_rules_sym : batch_rules);
-    auto cls = [&](int nf) { size_t c = 0; while (c < rules.size() && nf > rules[c].maxnf) ++c; return (int)c; };
+    // LDL^T fronts above dense_min rows take the one-scenario-per-CTA kernel with the FP64 tensor-core trailing update.
+    // Measured on the 10k-bus gain matrix (scripts/sweep_dense.sh, factor phase per increment): single case 2.25 ms off,
+    // 1.82 from 33 rows, 1.76 from 17 rows; 1000 draws 35.7 ms off, 33.7 from 65 rows, 34.9 from 49, 39.3 from 33 (below
+    // ~64 rows the scenario-tile kernels win in batches: they coalesce 2-16 scenarios per 256-byte line).
+    // JGB_DENSE_MIN overrides, 0 = off (tuning only)
+    static const int dense_env = getenv("JGB_DENSE_MIN") ? atoi(getenv("JGB_DENSE_MIN")) : -1;
+    const int dense_min = dense_env == 0 ? (1 << 30) : dense_env > 0 ? dense_env : (S == 1 ? 16 : 64);
+    auto dense_ok = [&](int nf) {
+        return symmetric && nf > dense_min && nf <= kMaxSymFront && dense_smem_doubles(nf) * sizeof(double) <= 220 * 1024;
+    };
+    auto cls0 = [&](int nf) { size_t c = 0; while (c < rules.size() && nf > rules[c].maxnf) ++c; return (int)c; };
+    auto cls = [&](int nf) { return dense_ok(nf) ? 1000 : cls0(nf); };      // dense fronts of a level share one launch
     build_tasks(S, 0);
     // level schedule of the fronts the task launches leave over
     plan_levelptr.assign(1, 0);
@@ -1167,26 +1184,6 @@ void MfSolver::plan(int S) {
         for (int q = sym.levelptr[l]; q < sym.levelptr[l + 1]; ++q)
             if (!in_task[sym.level_fronts[q]]) plan_fronts.push_back(sym.level_fronts[q]);
         plan_levelptr.push_back((int)plan_fronts.size());
-    }
-    {
-        std::vector<FrontDesc> descs(plan_fronts.size());
-        for (size_t q = 0; q < descs.size(); ++q) {
-            const int f = plan_fronts[q];
-            FrontDesc& d = descs[q];
-            d.f = f; d.nf = sym.f_nf[f]; d.k = sym.f_k[f]; d.rowptr = sym.f_rowptr[f];
-            d.asm0 = sym.f_asmptr[f]; d.asm1 = sym.f_asmptr[f + 1];
-            d.child0 = sym.f_childptr[f]; d.child1 = sym.f_childptr[f + 1];
-            d.ea0 = sym.f_eaptr[f]; d.ea1 = sym.f_eaptr[f + 1];
-            d.pad0 = d.pad1 = 0;
-            d.uoff = sym.f_uoff[f]; d.updoff = sym.f_updoff[f];
-        }
-        d_plan_desc.alloc(descs.size());
-        d_plan_fronts.alloc(plan_fronts.size());
-        if (!descs.empty()) {
-            JGB_CUDA(cudaMemcpy(d_plan_desc.p, descs.data(), descs.size() * sizeof(FrontDesc), cudaMemcpyHostToDevice));
-            JGB_CUDA(cudaMemcpy(d_plan_fronts.p, plan_fronts.data(), plan_fronts.size() * sizeof(int),
-                                cudaMemcpyHostToDevice));
-        }
     }
     for (int l = 0; l < sym.nlevels; ++l) {
         int b = plan_levelptr[l], e = plan_levelptr[l + 1];
@@ -1200,9 +1197,21 @@ void MfSolver::plan(int S) {
             FactorLaunch fl{};
             fl.begin = i;
             fl.count = j - i;
+            fl.dense = dense_ok(nf);
+            if (fl.dense) c = cls0(nf);
             fl.sym = symmetric && nf <= kMaxSymFront;
             fl.global_front = !fl.sym && (nf > kMaxSmemFront || c >= (int)rules.size());
             fl.bulk = false;
+            if (fl.dense) {
+                fl.ts = 1;
+                fl.threads = 256;
+                fl.smem = dense_smem_doubles(nf) * sizeof(double);
+                fl.tr = 1;
+                fl.gstride = 0;
+                fplan.push_back(fl);
+                i = j;
+                continue;
+            }
             if (!fl.global_front && S >= 32 && bulk_enabled && bulk_variant_for(nf) != 0) {
                 fl.maxnf = bulk_variant_for(nf);
                 // TMA-staged kernel: front + staging for the children's update blocks must fit in shared memory
@@ -1261,6 +1270,35 @@ void MfSolver::plan(int S) {
             if (fl.smem > 200 * 1024) throw std::runtime_error("front too large for shared memory");
             fplan.push_back(fl);
             i = j;
+        }
+    }
+    {
+        // per-front descriptors in launch order. Fronts factored on packed lower triangles (LDL^T kernels) take the
+        // symmetric gather lists, and a front whose parent is such a front writes only the lower triangle of its block.
+        std::vector<char> lower(sym.nfronts, 0);
+        for (const FactorLaunch& fl : fplan)
+            if ((fl.sym || fl.dense) && !fl.bulk)
+                for (int q = fl.begin; q < fl.begin + fl.count; ++q) lower[plan_fronts[q]] = 1;
+        std::vector<FrontDesc> descs(plan_fronts.size());
+        for (size_t q = 0; q < descs.size(); ++q) {
+            const int f = plan_fronts[q];
+            FrontDesc& d = descs[q];
+            d.f = f; d.nf = sym.f_nf[f]; d.k = sym.f_k[f]; d.rowptr = sym.f_rowptr[f];
+            d.asm0 = sym.f_asmptr[f]; d.asm1 = sym.f_asmptr[f + 1];
+            d.child0 = sym.f_childptr[f]; d.child1 = sym.f_childptr[f + 1];
+            if (lower[f]) { d.ea0 = sym.f_eaptr_sym[f]; d.ea1 = sym.f_eaptr_sym[f + 1]; }
+            else { d.ea0 = sym.f_eaptr[f]; d.ea1 = sym.f_eaptr[f + 1]; }
+            const int par = sym.f_parent[f];
+            d.flags = (par >= 0 && lower[par]) ? 1 : 0;
+            d.pad1 = 0;
+            d.uoff = sym.f_uoff[f]; d.updoff = sym.f_updoff[f];
+        }
+        d_plan_desc.alloc(descs.size());
+        d_plan_fronts.alloc(plan_fronts.size());
+        if (!descs.empty()) {
+            JGB_CUDA(cudaMemcpy(d_plan_desc.p, descs.data(), descs.size() * sizeof(FrontDesc), cudaMemcpyHostToDevice));
+            JGB_CUDA(cudaMemcpy(d_plan_fronts.p, plan_fronts.data(), plan_fronts.size() * sizeof(int),
+                                cudaMemcpyHostToDevice));
         }
     }
     // back-solve: one launch per depth level; batch launches are additionally cut by front size so that the
@@ -1348,7 +1386,10 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
                     rhs, d_U.p, d_upd.p, sym.upd_size, S, tl.front_cap, tl.stack_cap, active, status);
     for (const FactorLaunch& fl : fplan) {
         dim3 grid(fl.count, S / fl.ts);
-        if (fl.bulk)
+        if (fl.dense)
+            mf_factor_dense_sym_kernel<<<grid, fl.threads, fl.smem, st>>>(dev, d_plan_desc.p + fl.begin, aval, rhs, d_U.p,
+                                                                           d_upd.p, S, active, status);
+        else if (fl.bulk)
             launch_factor_bulk(fl.maxnf, grid, fl.smem, st, dev, d_plan_desc.p + fl.begin, aval, rhs, d_U.p,
                                d_upd.p, S, fl.smem_elems, active, status);
         else if (fl.global_front)
@@ -1356,7 +1397,7 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
                                 d_plan_desc.p + fl.begin, aval, rhs, d_U.p, d_upd.p, S, fl.tr,
                                 active, status, d_gwork.p, fl.gstride);
         else if (fl.sym)
-            launch_factor_sym(fl.ts, grid, fl.threads, fl.smem, st, dev, d_plan_fronts.p + fl.begin, aval, rhs, d_U.p,
+            launch_factor_sym(fl.ts, grid, fl.threads, fl.smem, st, dev, d_plan_desc.p + fl.begin, aval, rhs, d_U.p,
                               d_upd.p, S, fl.tr, active, status);
         else
             launch_factor<false>(fl.ts, grid, fl.threads, fl.smem, st, dev, d_plan_fronts.p + fl.begin,

@@ -16,6 +16,8 @@ struct DevSym {
     const int *f_k, *f_nf, *f_rowptr, *f_rows, *f_relptr, *f_rel, *f_childptr, *f_children, *f_asmptr, *asm_src,
         *asm_dst, *f_eaptr, *ea_roundptr;
     const int2* ea_pair;
+    const int* ea_roundptr_s;       // symmetric (packed lower triangle) gather lists, see symbolic.hpp
+    const int2* ea_pair_s;
     const long long *f_uoff, *f_updoff;
     long long upd_size;
     const struct ChildDesc* child_desc;
@@ -29,7 +31,8 @@ struct DevSym {
 struct __align__(16) FrontDesc {
     int f, nf, k, rowptr;
     int asm0, asm1, child0, child1;
-    int ea0, ea1, pad0, pad1;
+    int ea0, ea1;          // rounds of the extend-add gather (symmetric lists when the solver is symmetric)
+    int flags, pad1;       // flags bit 0: the parent reads only the lower triangle + rhs of this front's update block
     long long uoff, updoff;
 };
 
@@ -48,6 +51,7 @@ struct FactorLaunch {
     bool global_front;     // front kept in a global workspace instead of shared memory
     bool bulk;             // TMA-staged small-front kernel (batch only)
     bool sym;              // packed symmetric (LDL^T) kernel
+    bool dense;            // one-scenario-per-CTA LDL^T kernel with the tensor-core trailing update (mf_dense.cuh)
     int maxnf;             // bulk: register bound on the front order (kernel variant)
     int smem_elems;        // bulk: front + staging capacity in elements (x 32 lanes x 8 bytes)
     long long gstride;
@@ -108,7 +112,8 @@ class MfSolver {
     std::vector<FactorLaunch> fplan;
     std::vector<SolveLaunch> splan;
     DevBuf<int> d_f_k, d_f_nf, d_f_rowptr, d_f_rows, d_f_relptr, d_f_rel, d_f_childptr, d_f_children, d_f_asmptr,
-        d_asm_src, d_asm_dst, d_level_fronts, d_depth_fronts, d_f_eaptr, d_ea_roundptr, d_ea_pair;
+        d_asm_src, d_asm_dst, d_level_fronts, d_depth_fronts, d_f_eaptr, d_ea_roundptr, d_ea_pair, d_ea_roundptr_s,
+        d_ea_pair_s;
     DevBuf<long long> d_f_uoff, d_f_updoff;
     DevBuf<double> d_U, d_upd, d_gwork, d_cvec;
     DevBuf<long long> d_coff, d_zoff;

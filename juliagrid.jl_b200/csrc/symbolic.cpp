@@ -428,7 +428,29 @@ void analyse(int n, const int* colptr, const int* rowidx, const int* group, cons
                 S.ea_roundptr.push_back((int)(S.ea_pair.size() / 2));
             }
             S.f_eaptr[f + 1] = (int)S.ea_roundptr.size() - 1;
+            // symmetric variant: lower triangle + rhs only, packed destinations
+            if (f == 0) { S.f_eaptr_sym.assign(nf_total + 1, 0); S.ea_roundptr_sym.assign(1, 0); }
+            const int tri = nf * (nf + 1) / 2;
+            seen.assign((size_t)tri + nf, 0);
+            rounds.clear();
+            for (auto& pr : rec) {
+                const int c = pr.first / nf, r = pr.first - c * nf;
+                int dst;
+                if (c == nf) dst = tri + r;
+                else if (r >= c) dst = (c * (2 * nf - c + 1)) / 2 + r - c;
+                else continue;
+                int rr = seen[dst]++;
+                if ((int)rounds.size() <= rr) rounds.resize(rr + 1);
+                rounds[rr].push_back({dst, pr.second});
+            }
+            for (auto& rd : rounds) {
+                std::sort(rd.begin(), rd.end());
+                for (auto& pr : rd) { S.ea_pair_sym.push_back(pr.first); S.ea_pair_sym.push_back(pr.second); }
+                S.ea_roundptr_sym.push_back((int)(S.ea_pair_sym.size() / 2));
+            }
+            S.f_eaptr_sym[f + 1] = (int)S.ea_roundptr_sym.size() - 1;
         }
+        if (nf_total == 0) { S.f_eaptr_sym.assign(1, 0); S.ea_roundptr_sym.assign(1, 0); }
     }
     // ---- level schedules
     std::vector<int> height(nf_total, 0), depth(nf_total, 0);

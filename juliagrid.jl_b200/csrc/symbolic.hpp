@@ -71,6 +71,10 @@ struct Symbolic {
     std::vector<int> ea_roundptr;    // [nrounds+1] range of pairs of a round in ea_pair
     std::vector<int> ea_pair;        // 2 ints per pair: destination r + c*nf in the parent front, source element
                                      // offset into the update storage (f_updoff[child] + i + j*u_child)
+    // The same lists for a symmetric matrix factored on packed lower triangles: only destinations on or below the
+    // diagonal and the right-hand side, destination = packed index (column c at c*(2nf-c+1)/2, entry r-c; rhs entry r at
+    // nf(nf+1)/2 + r) — half the pairs, no index arithmetic in the kernels
+    std::vector<int> f_eaptr_sym, ea_roundptr_sym, ea_pair_sym;
     std::vector<int64_t> f_uoff;     // offset of the front's packed U rows (k rows, row p has nf+1-p entries)
     std::vector<int64_t> f_updoff;   // offset of the front's update block (u x (u+1), column major, last col = rhs)
     int64_t u_size = 0, upd_size = 0;

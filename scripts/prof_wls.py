@@ -12,8 +12,9 @@ jgb200.add_voltmeter(mon, a.voltage.magnitude); jgb200.add_wattmeter(mon, pw); j
 buses = np.sort(np.random.default_rng(7).choice(ps.n, ps.n // 10, replace=False))
 jgb200.add_pmu(mon, pw, a.voltage.magnitude, a.voltage.angle, buses=buses, polar=False)
 se = jgb200.gauss_newton(mon, ctx)
-print("increment", jgb200.increment(se))
-print("increment", jgb200.increment(se))
+if "batchonly" not in sys.argv:
+    print("increment", jgb200.increment(se))
+    print("increment", jgb200.increment(se))
 if len(sys.argv) > 2 and sys.argv[1] == "batch":
     # Monte-Carlo batch of S draws, iteration cap 1 (two increments): launch list of the batch kernels
     S = int(sys.argv[2])
