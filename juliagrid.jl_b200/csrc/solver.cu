@@ -609,9 +609,16 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
         if (p >= k) break;
         double* b = bc + (p & 1) * (MAXNF * 32) + sl;
         if (e0 == p % TE) {
+            // the warp that owns the pivot column publishes it and, while it holds it in registers, watches the pivot
+            // guard: largest entry below the pivot against growth * |pivot| (one compare per entry, this warp only)
+            double mx = 0.0;
 #pragma unroll
             for (int i = p; i < MAXNF; ++i)
-                if (i < nf) b[i * 32] = col[p / TE][i];
+                if (i < nf) {
+                    b[i * 32] = col[p / TE][i];
+                    if (i > p) mx = fmax(mx, fabs(col[p / TE][i]));
+                }
+            if (mx > sy.growth * fabs(col[p / TE][p])) weakp = true;
         }
         __syncthreads();
         const double piv = b[p * 32];
@@ -627,11 +634,9 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
             if (act && in) Urow[wide(c - p, S)] = (c == p) ? inv : upc;
             m[q] = (in && c > p) ? inv * upc : 0.0;
         }
-        const bool chk = e0 == p % TE;                  // one warp per pivot watches the multipliers
 #pragma unroll
         for (int i = p + 1; i < MAXNF; ++i) {
             const double li = (i < nf) ? b[i * 32] : 0.0;   // pivot-column entry, read once for all owned columns
-            if (chk && fabs(li * inv) > sy.growth) weakp = true;
 #pragma unroll
             for (int q = 0; q < NC; ++q) col[q][i] -= li * m[q];
         }
