@@ -16,10 +16,9 @@ if mode == "single":
         jgb200.power_flow(a)
     print("iters", a.method.iteration)
 else:
-    mdl = ps.model
-    ks = np.arange(S) % ps.nbr
-    of = i64(ps.frm[ks] + 1); ot = i64(ps.to[ks] + 1)
-    dy = np.ascontiguousarray(np.stack([mdl.y_ff[ks], mdl.y_ft[ks], mdl.y_tf[ks], mdl.y_tt[ks]], axis=1)).view(np.float64).reshape(S, 8)
+    elig = jgb200.eligible_outages(ps)          # the sweep of the benchmark: bridges (islanding outages) are not part of it
+    ks = elig[np.arange(S) % len(elig)]
+    of, ot, dy = jgb200.outage_arrays(ps, ks)
     vm = np.empty((S, ps.n)); va = np.empty((S, ps.n)); it = np.empty(S, dtype=np.int32); st = np.empty(S, dtype=np.int8)
     tot = C.c_int64(0)
     rc = ctx.lib.jgb_nr_batch(ctx.handle, S, ptr(of, C.c_int64), ptr(ot, C.c_int64), ptr(dy, C.c_double), 2, 1e-8,
