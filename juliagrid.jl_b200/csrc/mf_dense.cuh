@@ -59,8 +59,8 @@ mf_factor_dense_sym_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const
     // scattered loads are in flight together; the matrix entries and the rhs are added once the copies have landed, then
     // the remaining rounds (symmetric lists: lower triangle + rhs, packed destinations; the rhs vector follows the
     // triangle in shared memory, so one index addresses both).
-    const int W = S < 32 ? S : 32;
-    double* __restrict__ up = upd + (long long)(s / W) * sy.upd_size * W + (s % W);
+    constexpr int W = 1;                         // this kernel reads its children in the W = 1 section: contiguous per scenario
+    double* __restrict__ up = upd_base(upd, sy, 1, s);
     if (fd.ea1 > fd.ea0) {
         const int t1 = sy.ea_roundptr_s[fd.ea0 + 1];
         for (int t = sy.ea_roundptr_s[fd.ea0] + tid; t < t1; t += nth) {
@@ -219,17 +219,18 @@ mf_factor_dense_sym_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const
             Urow[wide(j - p, S)] = (j == p) ? 1.0 / v : v;
         }
     }
-    double* __restrict__ Cf = up + fd.updoff * W;
+    const int Wo = fd.wout;                     // the parent's tile width (1 when the parent is a dense front: contiguous)
+    double* __restrict__ Cf = upd_base(upd, sy, Wo, s) + fd.updoff * Wo;
     const bool lower_only = fd.flags & 1;       // the parent is an LDL^T front too: it never reads above the diagonal
     for (int j = warp; j <= u; j += nwarps) {   // one warp per column of the block: no index division
-        double* Cj = Cf + (unsigned)(j * u * W);
+        double* Cj = Cf + (unsigned)(j * u * Wo);
         if (j == u) {
-            for (int i = lane; i < u; i += 32) Cj[(unsigned)(i * W)] = R[k + i];
+            for (int i = lane; i < u; i += 32) Cj[(unsigned)(i * Wo)] = R[k + i];
         } else {
             const double* colj = F + sym_col(k + j, nf) - j;          // entry (k + i, k + j), i >= j, at colj[i]
-            for (int i = j + lane; i < u; i += 32) Cj[(unsigned)(i * W)] = colj[i];
+            for (int i = j + lane; i < u; i += 32) Cj[(unsigned)(i * Wo)] = colj[i];
             if (!lower_only)
-                for (int i = lane; i < j; i += 32) Cj[(unsigned)(i * W)] = F[sym_col(k + i, nf) + j - i];
+                for (int i = lane; i < j; i += 32) Cj[(unsigned)(i * Wo)] = F[sym_col(k + i, nf) + j - i];
         }
     }
 }

@@ -18,7 +18,7 @@
 //   [0] number of fronts; then kTaskRec ints per front:
 //   0 nf, 1 k, 2 offset of the entry lists, 3 offset of the child records, 4 number of children,
 //   5 stack offset of the update block in elements (-1: task root, block goes to HBM), 6/7 packed-U offset lo/hi,
-//   8/9 update-storage offset lo/hi
+//   8/9 update-storage offset lo/hi, 10 tile width of the section a root's block goes to (its parent's launch width)
 //   entry lists: TE + 1 sublist offsets (in pairs, relative), then (source, destination) pairs; source >= 0 indexes the
 //   matrix values, source < 0 the right-hand side (-source - 1); destination = r + c * nf
 //   child record: uc, stack offset (-1: block in HBM), update-storage offset lo/hi, then uc relative indices
@@ -26,7 +26,7 @@ constexpr int kTaskPre = 8;        // matrix entries per thread fetched one fron
 
 template <int TE, int M>
 __device__ __forceinline__ void task_eliminate(const double* Fl, double* bcl, int nf, int k, int e0, bool act,
-                                               double* __restrict__ Uf, int S, double* ub, bool& bad) {
+                                               double* __restrict__ Uf, int S, double* ub, int ust, bool& bad) {
     constexpr int NC = (M + 1 + TE - 1) / TE;
     double col[NC][M];
 #pragma unroll
@@ -70,19 +70,19 @@ __device__ __forceinline__ void task_eliminate(const double* Fl, double* bcl, in
     for (int q = 0; q < NC; ++q) {
         const int c = e0 + q * TE;
         if (c >= k && c <= nf) {
-            double* Cj = ub + (c - k) * u * 32;
+            double* Cj = ub + (unsigned)((c - k) * u * ust);
 #pragma unroll
             for (int i = 0; i < M; ++i)
-                if (i >= k && i < nf) Cj[(i - k) * 32] = col[q][i];
+                if (i >= k && i < nf) Cj[(unsigned)((i - k) * ust)] = col[q][i];
         }
     }
 }
 
 template <int TE, int MAXNF>
 __global__ void __launch_bounds__(32 * TE)
-mf_task_kernel(const int* __restrict__ blobs, const int2* __restrict__ tasks, const double* __restrict__ aval,
-               const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, long long upd_size,
-               int S, int front_cap, int stack_cap, const unsigned char* __restrict__ active,
+mf_task_kernel(DevSym sy, const int* __restrict__ blobs, const int2* __restrict__ tasks,
+               const double* __restrict__ aval, const double* __restrict__ rhs, double* __restrict__ U,
+               double* __restrict__ upd, int S, int front_cap, int stack_cap, const unsigned char* __restrict__ active,
                int* __restrict__ status) {
     extern __shared__ __align__(128) double sm[];
     const int sl = threadIdx.x & 31, e0 = threadIdx.x >> 5;
@@ -99,7 +99,8 @@ mf_task_kernel(const int* __restrict__ blobs, const int2* __restrict__ tasks, co
     const int nfr = meta[0];
     const double* __restrict__ av = aval + s;
     const double* __restrict__ rv = rhs + s;
-    double* __restrict__ uptile = upd + (long long)blockIdx.y * upd_size * 32 + sl;
+    // blocks read from HBM (children outside the task) live in the section of tile width 32 of the update storage
+    double* __restrict__ uptile = upd + sy.sec_base[5] + (long long)blockIdx.y * sy.sec_size[5] * 32 + sl;
     double pv[kTaskPre];
     bool bad = false;
 
@@ -172,17 +173,22 @@ mf_task_kernel(const int* __restrict__ blobs, const int2* __restrict__ tasks, co
         const long long uoff = ((long long)fr[7] << 32) | (unsigned)fr[6];
         double* __restrict__ Uf = U + uoff * S + s;
         double* ub;
-        if (fr[5] >= 0) ub = stk + fr[5] * 32;
-        else ub = uptile + (((long long)fr[9] << 32) | (unsigned)fr[8]) * 32;
+        int ust = 32;
+        if (fr[5] >= 0) {
+            ub = stk + fr[5] * 32;
+        } else {                                  // task root: the block goes to the section its parent reads
+            ust = fr[10];
+            ub = upd_base(upd, sy, ust, s) + (((long long)fr[9] << 32) | (unsigned)fr[8]) * ust;
+        }
         if constexpr (MAXNF > 12) {
-            if (nf > 12) task_eliminate<TE, 16>(Fl, bcl, nf, k, e0, act, Uf, S, ub, bad);
-            else if (nf > 8) task_eliminate<TE, 12>(Fl, bcl, nf, k, e0, act, Uf, S, ub, bad);
-            else task_eliminate<TE, 8>(Fl, bcl, nf, k, e0, act, Uf, S, ub, bad);
+            if (nf > 12) task_eliminate<TE, 16>(Fl, bcl, nf, k, e0, act, Uf, S, ub, ust, bad);
+            else if (nf > 8) task_eliminate<TE, 12>(Fl, bcl, nf, k, e0, act, Uf, S, ub, ust, bad);
+            else task_eliminate<TE, 8>(Fl, bcl, nf, k, e0, act, Uf, S, ub, ust, bad);
         } else if constexpr (MAXNF > 8) {
-            if (nf > 8) task_eliminate<TE, 12>(Fl, bcl, nf, k, e0, act, Uf, S, ub, bad);
-            else task_eliminate<TE, 8>(Fl, bcl, nf, k, e0, act, Uf, S, ub, bad);
+            if (nf > 8) task_eliminate<TE, 12>(Fl, bcl, nf, k, e0, act, Uf, S, ub, ust, bad);
+            else task_eliminate<TE, 8>(Fl, bcl, nf, k, e0, act, Uf, S, ub, ust, bad);
         } else {
-            task_eliminate<TE, 8>(Fl, bcl, nf, k, e0, act, Uf, S, ub, bad);
+            task_eliminate<TE, 8>(Fl, bcl, nf, k, e0, act, Uf, S, ub, ust, bad);
         }
         __syncthreads();
     }
@@ -191,13 +197,13 @@ mf_task_kernel(const int* __restrict__ blobs, const int2* __restrict__ tasks, co
 
 #define JGB_TASK_VARIANTS(X) X(4, 8) X(4, 12) X(8, 16)
 
-void launch_task(int te, int maxnf, dim3 grid, size_t smem, cudaStream_t st, const int* blobs, const int2* tasks,
-                 const double* aval, const double* rhs, double* U, double* upd, long long upd_size, int S,
+void launch_task(int te, int maxnf, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const int* blobs,
+                 const int2* tasks, const double* aval, const double* rhs, double* U, double* upd, int S,
                  int front_cap, int stack_cap, const unsigned char* active, int* status) {
 #define X(TE, MAXNF)                                                                                                \
     if (te == TE && maxnf == MAXNF) {                                                                               \
-        mf_task_kernel<TE, MAXNF><<<grid, 32 * TE, smem, st>>>(blobs, tasks, aval, rhs, U, upd, upd_size, S,        \
-                                                               front_cap, stack_cap, active, status);              \
+        mf_task_kernel<TE, MAXNF><<<grid, 32 * TE, smem, st>>>(dev, blobs, tasks, aval, rhs, U, upd, S, front_cap,  \
+                                                               stack_cap, active, status);                         \
         return;                                                                                                     \
     }
     JGB_TASK_VARIANTS(X)

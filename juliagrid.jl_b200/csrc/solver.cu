@@ -18,6 +18,13 @@ namespace {
 // multiply (mul.wide.u32) or stay in 32 bits, instead of sign-extended 64-bit multiply sequences.
 __device__ __forceinline__ size_t wide(int a, int b) { return (size_t)(unsigned)a * (unsigned)b; }
 
+// log2 of a power-of-two tile width (1..32)
+__host__ __device__ __forceinline__ int lg2(int w) { return w >= 32 ? 5 : w >= 16 ? 4 : w >= 8 ? 3 : w >= 4 ? 2 : w >= 2 ? 1 : 0; }
+// base of scenario s in the update-storage section of tile width W (see DevSym): add (off + e) * W for an element
+__device__ __forceinline__ double* upd_base(double* upd, const DevSym& sy, int W, int s) {
+    const int lw = lg2(W);
+    return upd + sy.sec_base[lw] + (long long)(s / W) * sy.sec_size[lw] * W + (s % W);
+}
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ long long urow_off(int p, int nf) {
@@ -55,15 +62,16 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
         fd.asm0 = sy.f_asmptr[f]; fd.asm1 = sy.f_asmptr[f + 1];
         fd.ea0 = sy.f_eaptr[f]; fd.ea1 = sy.f_eaptr[f + 1];
         fd.child0 = fd.child1 = 0;
+        fd.wout = S < 32 ? S : 32;
         fd.uoff = sy.f_uoff[f]; fd.updoff = sy.f_updoff[f];
     }
     const int nf = fd.nf, k = fd.k, u = nf - k;
     const int* __restrict__ rows = sy.f_rows + fd.rowptr;
     const int total = nf * (nf + 1);
 
-    // update storage is tile major: element e of scenario s at [((s / W) * upd_size + e) * W + s % W], W = min(S, 32)
-    const int W = S < 32 ? S : 32;
-    double* __restrict__ up = upd + (long long)(s / W) * sy.upd_size * W + (s % W);
+    // the children's blocks live in the update-storage section of this launch's tile width (see DevSym)
+    constexpr int W = TS;
+    double* __restrict__ up = upd_base(upd, sy, TS, s);
     for (int pos = e0; pos < total; pos += TE) Fl[pos * TS] = 0.0;
     __syncthreads();
     // Round 0 of the extend-add (the first source of every destination — for the fronts at the top of the tree that is
@@ -277,11 +285,12 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
             Urow[wide(j - p, S)] = (j == p) ? 1.0 / v : v;
         }
     }
-    double* __restrict__ Cf = up + fd.updoff * W;
+    const int Wo = fd.wout;                     // the parent's tile width
+    double* __restrict__ Cf = upd_base(upd, sy, Wo, s) + fd.updoff * Wo;
     for (int j = ec; j <= u; j += TC) {
         const double* colj = Fl + ((k + j) * nf + k) * TS;
-        double* Cj = Cf + (unsigned)(j * u * W);
-        for (int i = er; i < u; i += TR) Cj[(unsigned)(i * W)] = colj[i * TS];
+        double* Cj = Cf + (unsigned)(j * u * Wo);
+        for (int i = er; i < u; i += TR) Cj[(unsigned)(i * Wo)] = colj[i * TS];
     }
 }
 
@@ -329,8 +338,8 @@ mf_factor_sym_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doubl
         for (int p = e0; p < k; p += TE) Rl[p * TS] = rhs[wide(rows[p], S) + s];
     }
     __syncthreads();
-    const int W = S < 32 ? S : 32;
-    double* __restrict__ up = upd + (long long)(s / W) * sy.upd_size * W + (s % W);
+    constexpr int W = TS;
+    double* __restrict__ up = upd_base(upd, sy, TS, s);
     // gather of the children's blocks in rounds over the symmetric lists: lower triangle + rhs only, packed destinations
     // (the rhs vector follows the triangle, so one index addresses both)
     for (int rd = fd.ea0; rd < fd.ea1; ++rd) {
@@ -411,10 +420,11 @@ mf_factor_sym_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doubl
             Urow[wide(j - p, S)] = (j == p) ? 1.0 / v : v;
         }
     }
-    double* __restrict__ Cf = up + fd.updoff * W;
+    const int Wo = fd.wout;
+    double* __restrict__ Cf = upd_base(upd, sy, Wo, s) + fd.updoff * Wo;
     const bool lower_only = fd.flags & 1;       // the parent is an LDL^T front too: it never reads above the diagonal
     for (int j = ec; j <= u; j += TC) {
-        double* Cj = Cf + (unsigned)(j * u * W);
+        double* Cj = Cf + (unsigned)(j * u * Wo);
         for (int i = (lower_only && j < u) ? j + ((er - j % TR + TR) % TR) : er; i < u; i += TR) {
             double v;
             if (j == u) v = Rl[(k + i) * TS];
@@ -422,7 +432,7 @@ mf_factor_sym_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doubl
                 const int r = i >= j ? i : j, c = i >= j ? j : i;
                 v = Fl[(sym_col(k + c, nf) + r - c) * TS];
             }
-            Cj[(unsigned)(i * W)] = v;
+            Cj[(unsigned)(i * Wo)] = v;
         }
     }
 }
@@ -497,7 +507,7 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
     double* stage = sm + fsz * 32;
     const int cap = smem_elems - fsz;
     int* srel = reinterpret_cast<int*>(sm + (size_t)smem_elems * 32);
-    double* __restrict__ uptile = upd + (long long)blockIdx.y * sy.upd_size * 32;
+    double* __restrict__ uptile = upd + sy.sec_base[5] + (long long)blockIdx.y * sy.sec_size[5] * 32;   // section W = 32
     const int c0 = fd.child0, c1 = fd.child1;
 
     if (threadIdx.x == 0 && c1 > c0) mbar_init(&mbar, 1);
@@ -644,15 +654,16 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
     if (!act) return;
     if (bad && e0 == 0) status[s] = -3;
     if (weakp && sy.weak) sy.weak[s] = 1;
-    double* __restrict__ Cf = uptile + fd.updoff * 32 + sl;
+    const int Wo = fd.wout;                     // the parent's tile width (32 when the parent is a small front too)
+    double* __restrict__ Cf = upd_base(upd, sy, Wo, s) + fd.updoff * Wo;
 #pragma unroll
     for (int q = 0; q < NC; ++q) {
         const int c = e0 + q * TE;
         if (c >= k && c <= nf) {
-            double* Cj = Cf + (unsigned)((c - k) * u * 32);
+            double* Cj = Cf + (unsigned)((c - k) * u * Wo);
 #pragma unroll
             for (int i = 0; i < MAXNF; ++i)
-                if (i >= k && i < nf) Cj[(i - k) * 32] = col[q][i];
+                if (i >= k && i < nf) Cj[(unsigned)((i - k) * Wo)] = col[q][i];
         }
     }
 }
@@ -1094,6 +1105,7 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
     JGB_CUDA(cudaFuncSetAttribute(mf_factor_dense_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     dev.upd_size = sym.upd_size;
     dev.child_desc = d_child_desc.p;
+    for (int q = 0; q < 6; ++q) { dev.sec_base[q] = 0; dev.sec_size[q] = sym.upd_size; }
     dev.weak = nullptr;
     dev.growth = 1e300;
     JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1122,24 +1134,21 @@ std::vector<PlanRule> parse_rules(const char* env, const std::vector<PlanRule>& 
 
 void MfSolver::build_tasks(int S, cudaStream_t) {
     tplan.clear();
+    task_plan = TaskPlan();
     in_task.assign(sym.nfronts, 0);
     task_fronts = task_count = 0;
     task_upd_on_chip = 0;
     if (S < 32 || S % 32 != 0) return;
-    TaskPlan tp;
-    partition_tasks(sym, task_options_from_env(), tp);
-    if (tp.launches.empty()) return;
-    tplan = tp.launches;
-    in_task = tp.in_task;
-    task_fronts = tp.task_fronts;
-    task_count = tp.task_count;
-    task_upd_on_chip = tp.upd_on_chip;
+    partition_tasks(sym, task_options_from_env(), task_plan);
+    if (task_plan.launches.empty()) return;
+    tplan = task_plan.launches;
+    in_task = task_plan.in_task;
+    task_fronts = task_plan.task_fronts;
+    task_count = task_plan.task_count;
+    task_upd_on_chip = task_plan.upd_on_chip;
     for (TaskLaunch& tl : tplan)
         if (tl.smem > 220 * 1024) throw std::runtime_error("task kernel: shared-memory budget exceeded");
-    d_task_blob.alloc(tp.blob.size());
-    d_task_desc.alloc(tp.descs.size() / 2);
-    JGB_CUDA(cudaMemcpy(d_task_blob.p, tp.blob.data(), tp.blob.size() * sizeof(int), cudaMemcpyHostToDevice));
-    JGB_CUDA(cudaMemcpy(d_task_desc.p, tp.descs.data(), tp.descs.size() * sizeof(int), cudaMemcpyHostToDevice));
+    // the blobs are uploaded by plan() once the update-storage layout is fixed (offsets patched in)
 }
 
 void MfSolver::plan(int S) {
@@ -1284,12 +1293,89 @@ void MfSolver::plan(int S) {
         }
     }
     {
+        // Tile width of every front's launch, and with it the section of the update storage each block goes to: the
+        // block of front f is written at the width its PARENT reads with (see DevSym).
+        const int F = sym.nfronts;
+        const int wmax = S < 32 ? S : 32;
+        std::vector<int> ts_of(F, wmax);
+        std::vector<char> lower(F, 0);
+        for (const FactorLaunch& fl : fplan)
+            for (int q = fl.begin; q < fl.begin + fl.count; ++q) {
+                const int f = plan_fronts[q];
+                ts_of[f] = fl.bulk ? wmax : fl.ts;
+                if ((fl.sym || fl.dense) && !fl.bulk) lower[f] = 1;
+            }
+        std::vector<int> wout(F, wmax);
+        std::vector<long long> off(F, 0), secsz(6, 0);
+        for (int f = 0; f < F; ++f) {
+            const int par = sym.f_parent[f];
+            wout[f] = par < 0 ? wmax : ts_of[par];
+            const long long u = sym.f_nf[f] - sym.f_k[f];
+            off[f] = secsz[lg2(wout[f])];
+            secsz[lg2(wout[f])] += u * (u + 1);
+        }
+        long long base = 0;
+        for (int q = 0; q < 6; ++q) {
+            dev.sec_base[q] = base * S;
+            dev.sec_size[q] = secsz[q];
+            base += secsz[q];
+            if (secsz[q] >= (1LL << 31) / 32) throw std::runtime_error("update-storage section exceeds the 32-bit element offsets");
+        }
+        if (!tplan.empty()) {          // task blobs: update-storage offsets and root tile widths of this layout
+            std::vector<int> blob(task_plan.blob);
+            for (size_t q = 0; q < task_plan.off_pos.size(); ++q) {
+                const long long o = off[task_plan.off_front[q]];
+                blob[task_plan.off_pos[q]] = (int)(o & 0xffffffffLL);
+                blob[task_plan.off_pos[q] + 1] = (int)(o >> 32);
+            }
+            for (size_t q = 0; q < task_plan.wout_pos.size(); ++q) blob[task_plan.wout_pos[q]] = wout[task_plan.wout_front[q]];
+            d_task_blob.alloc(blob.size());
+            d_task_desc.alloc(task_plan.descs.size() / 2);
+            JGB_CUDA(cudaMemcpy(d_task_blob.p, blob.data(), blob.size() * sizeof(int), cudaMemcpyHostToDevice));
+            JGB_CUDA(cudaMemcpy(d_task_desc.p, task_plan.descs.data(), task_plan.descs.size() * sizeof(int),
+                                cudaMemcpyHostToDevice));
+        }
+        // gather lists with the source offsets of this layout: a pair's source is (child block offset + element)
+        auto remap = [&](const std::vector<int>& eaptr, const std::vector<int>& roundptr, const std::vector<int>& pairs,
+                         DevBuf<int>& out) {
+            std::vector<int> np(pairs);
+            for (int f = 0; f < F; ++f) {
+                const int c0 = sym.f_childptr[f], c1 = sym.f_childptr[f + 1];
+                if (c0 == c1) continue;
+                for (int t = roundptr[eaptr[f]]; t < roundptr[eaptr[f + 1]]; ++t) {
+                    const long long src = pairs[2 * t + 1];
+                    int lo = c0, hi = c1 - 1;               // children ascend in index and in f_updoff
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) / 2;
+                        if (sym.f_updoff[sym.f_children[mid]] <= src) lo = mid; else hi = mid - 1;
+                    }
+                    const int c = sym.f_children[lo];
+                    np[2 * t + 1] = (int)(off[c] + (src - sym.f_updoff[c]));
+                }
+            }
+            out.alloc(np.size());
+            if (!np.empty()) JGB_CUDA(cudaMemcpy(out.p, np.data(), np.size() * sizeof(int), cudaMemcpyHostToDevice));
+        };
+        remap(sym.f_eaptr, sym.ea_roundptr, sym.ea_pair, d_plan_pair);
+        dev.ea_pair = reinterpret_cast<const int2*>(d_plan_pair.p);
+        if (symmetric) {
+            remap(sym.f_eaptr_sym, sym.ea_roundptr_sym, sym.ea_pair_sym, d_plan_pair_s);
+            dev.ea_pair_s = reinterpret_cast<const int2*>(d_plan_pair_s.p);
+        }
+        {
+            std::vector<ChildDesc> cds(sym.f_children.size());
+            for (size_t q = 0; q < cds.size(); ++q) {
+                const int c = sym.f_children[q];
+                cds[q].uc = sym.f_nf[c] - sym.f_k[c];
+                cds[q].relptr = sym.f_relptr[c];
+                cds[q].updoff = off[c];
+            }
+            d_plan_child.alloc(cds.size());
+            if (!cds.empty()) JGB_CUDA(cudaMemcpy(d_plan_child.p, cds.data(), cds.size() * sizeof(ChildDesc), cudaMemcpyHostToDevice));
+            dev.child_desc = d_plan_child.p;
+        }
         // per-front descriptors in launch order. Fronts factored on packed lower triangles (LDL^T kernels) take the
         // symmetric gather lists, and a front whose parent is such a front writes only the lower triangle of its block.
-        std::vector<char> lower(sym.nfronts, 0);
-        for (const FactorLaunch& fl : fplan)
-            if ((fl.sym || fl.dense) && !fl.bulk)
-                for (int q = fl.begin; q < fl.begin + fl.count; ++q) lower[plan_fronts[q]] = 1;
         std::vector<FrontDesc> descs(plan_fronts.size());
         for (size_t q = 0; q < descs.size(); ++q) {
             const int f = plan_fronts[q];
@@ -1301,8 +1387,8 @@ void MfSolver::plan(int S) {
             else { d.ea0 = sym.f_eaptr[f]; d.ea1 = sym.f_eaptr[f + 1]; }
             const int par = sym.f_parent[f];
             d.flags = (par >= 0 && lower[par]) ? 1 : 0;
-            d.pad1 = 0;
-            d.uoff = sym.f_uoff[f]; d.updoff = sym.f_updoff[f];
+            d.wout = wout[f];
+            d.uoff = sym.f_uoff[f]; d.updoff = off[f];
         }
         d_plan_desc.alloc(descs.size());
         d_plan_fronts.alloc(plan_fronts.size());
@@ -1393,8 +1479,8 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
                             int* status, cudaStream_t st, cudaEvent_t after_factor) {
     plan(S);
     for (const TaskLaunch& tl : tplan)
-        launch_task(tl.te, tl.maxnf, dim3(tl.count, S / 32), tl.smem, st, d_task_blob.p, d_task_desc.p + tl.begin, aval,
-                    rhs, d_U.p, d_upd.p, sym.upd_size, S, tl.front_cap, tl.stack_cap, active, status);
+        launch_task(tl.te, tl.maxnf, dim3(tl.count, S / 32), tl.smem, st, dev, d_task_blob.p, d_task_desc.p + tl.begin,
+                    aval, rhs, d_U.p, d_upd.p, S, tl.front_cap, tl.stack_cap, active, status);
     for (const FactorLaunch& fl : fplan) {
         dim3 grid(fl.count, S / fl.ts);
         if (fl.dense)

@@ -20,6 +20,11 @@ struct DevSym {
     const int2* ea_pair_s;
     const long long *f_uoff, *f_updoff;
     long long upd_size;
+    // Update storage: one section per tile width W = 1, 2, 4, 8, 16, 32 (index log2 W). The block a front leaves for its
+    // parent lives in the section of the PARENT's scenario-tile width, so a CTA of TS scenarios reads its children and
+    // writes its own block as contiguous runs: element e of scenario s of a block at offset `off` of section W sits at
+    //   sec_base[lw] + ((s / W) * sec_size[lw] + off + e) * W + s % W          (sec_size in elements per scenario)
+    long long sec_base[6], sec_size[6];
     const struct ChildDesc* child_desc;
     // pivot guard (LU without pivoting): a multiplier |F[i,p] / F[p,p]| above `growth` marks the scenario in weak[] (nullable);
     // the caller then refines the solution of that scenario with one residual step
@@ -32,7 +37,8 @@ struct __align__(16) FrontDesc {
     int f, nf, k, rowptr;
     int asm0, asm1, child0, child1;
     int ea0, ea1;          // rounds of the extend-add gather (symmetric lists when the solver is symmetric)
-    int flags, pad1;       // flags bit 0: the parent reads only the lower triangle + rhs of this front's update block
+    int flags, wout;       // flags bit 0: the parent reads only the lower triangle + rhs of this front's update block;
+                           // wout: tile width of the section this front's block is written to (the parent's TS)
     long long uoff, updoff;
 };
 
@@ -102,9 +108,11 @@ class MfSolver {
     void plan(int S);
     void build_tasks(int S, cudaStream_t st);
     std::vector<TaskLaunch> tplan;
+    TaskPlan task_plan;
     std::vector<char> in_task;             // front is factored by a task launch (not by fplan)
     std::vector<int> plan_levelptr, plan_fronts;   // level schedule of the fronts left to fplan
-    DevBuf<int> d_task_blob, d_plan_fronts;
+    DevBuf<int> d_task_blob, d_plan_fronts, d_plan_pair, d_plan_pair_s;
+    DevBuf<ChildDesc> d_plan_child;
     DevBuf<int2> d_task_desc;
     DevBuf<FrontDesc> d_plan_desc;
     int planned_S = -1;

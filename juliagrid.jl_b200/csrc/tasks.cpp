@@ -186,6 +186,8 @@ void partition_tasks(const Symbolic& sym, const TaskOptions& opt, TaskPlan& out)
                 if (inside) out.upd_on_chip += (long long)uc * (uc + 1);
                 blob.push_back(uc);
                 blob.push_back(inside ? stack_off[c] : -1);
+                out.off_pos.push_back((int)blob.size());
+                out.off_front.push_back(c);
                 blob.push_back((int)(sym.f_updoff[c] & 0xffffffffLL));
                 blob.push_back((int)(sym.f_updoff[c] >> 32));
                 for (int i = 0; i < uc; ++i) blob.push_back(sym.f_rel[sym.f_relptr[c] + i]);
@@ -204,6 +206,11 @@ void partition_tasks(const Symbolic& sym, const TaskOptions& opt, TaskPlan& out)
             rec[5] = (f != r) ? stack_off[f] : -1;
             rec[6] = (int)(sym.f_uoff[f] & 0xffffffffLL); rec[7] = (int)(sym.f_uoff[f] >> 32);
             rec[8] = (int)(sym.f_updoff[f] & 0xffffffffLL); rec[9] = (int)(sym.f_updoff[f] >> 32);
+            rec[10] = 32;
+            out.off_pos.push_back((int)(rec0 + q * kTaskRec + 8));
+            out.off_front.push_back(f);
+            out.wout_pos.push_back((int)(rec0 + q * kTaskRec + 10));
+            out.wout_front.push_back(f);
         }
         if (sp != 0) throw std::logic_error("task stack not empty at the end of a task list");
         while ((blob.size() - start) % 4) blob.push_back(0);

@@ -9,7 +9,7 @@
 
 namespace jgb {
 
-constexpr int kTaskRec = 10;       // ints per front record in a task blob (layout: mf_task.cuh)
+constexpr int kTaskRec = 12;       // ints per front record in a task blob (layout: mf_task.cuh)
 
 // One launch of the task kernel: `count` CTAs per scenario tile, each walking one task list
 struct TaskLaunch {
@@ -39,6 +39,10 @@ struct TaskPlan {
     std::vector<int> blob;              // all task blobs
     std::vector<int> descs;             // 2 ints per task: blob offset, blob length
     std::vector<char> in_task;          // per front
+    // places in `blob` that hold an update-storage offset (lo word; hi word follows) or a tile width, with the front they
+    // refer to: MfSolver::plan patches them once the layout of the update storage is known (the blob as built here
+    // addresses the plain layout of Symbolic::f_updoff at tile width 32, which is what the host replay walks)
+    std::vector<int> off_pos, off_front, wout_pos, wout_front;
     int task_fronts = 0, task_count = 0;
     long long upd_on_chip = 0;          // update-block elements per scenario that never leave shared memory
 };
