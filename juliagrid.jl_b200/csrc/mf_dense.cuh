@@ -210,13 +210,14 @@ mf_factor_dense_sym_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const
     }
     if (bad && tid == 0) status[s] = -3;
     // ---- packed U rows (1 / d_p, then d_p L[j,p] = W[j,p], then the forward-substituted rhs) and the update block
-    double* __restrict__ Uf = U + fd.uoff * S + s;
+    const int Wu = (fd.flags >> 8) & 0xff;      // tile width of the back-solve launch that reads these rows (1: contiguous)
+    double* __restrict__ Uf = u_base(U, sy, Wu, s) + fd.uoff * Wu;
     for (int p = warp; p < k; p += nwarps) {
-        double* Urow = Uf + urow_off(p, nf) * S;
+        double* Urow = Uf + urow_off(p, nf) * Wu;
         const double* colp = F + sym_col(p, nf) - p;
         for (int j = p + lane; j <= nf; j += 32) {
             const double v = (j < nf) ? colp[j] : R[p];
-            Urow[wide(j - p, S)] = (j == p) ? 1.0 / v : v;
+            Urow[(unsigned)((j - p) * Wu)] = (j == p) ? 1.0 / v : v;
         }
     }
     const int Wo = fd.wout;                     // the parent's tile width (1 when the parent is a dense front: contiguous)

@@ -48,14 +48,14 @@ __device__ __forceinline__ void task_eliminate(const double* Fl, double* bcl, in
         const double piv = b[p * 32];
         if (piv == 0.0 || !isfinite(piv)) bad = true;
         const double inv = 1.0 / piv;
-        double* Urow = Uf + urow_off(p, nf) * S;
+        double* Urow = Uf + urow_off(p, nf) * 32;      // packed U rows of task fronts: section of tile width 32
         double m[NC];                                   // multiplier of each owned column, 0 for columns not updated
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
             const int c = e0 + q * TE;
             const double upc = col[q][p];               // U[p, c]
             const bool in = c >= p && c <= nf;
-            if (act && in) Urow[wide(c - p, S)] = (c == p) ? inv : upc;
+            if (act && in) Urow[(c - p) * 32] = (c == p) ? inv : upc;
             m[q] = (in && c > p) ? inv * upc : 0.0;
         }
 #pragma unroll
@@ -171,7 +171,7 @@ mf_task_kernel(DevSym sy, const int* __restrict__ blobs, const int2* __restrict_
             cp += 4 + uc;
         }
         const long long uoff = ((long long)fr[7] << 32) | (unsigned)fr[6];
-        double* __restrict__ Uf = U + uoff * S + s;
+        double* __restrict__ Uf = u_base(U, sy, 32, s) + uoff * 32;
         double* ub;
         int ust = 32;
         if (fr[5] >= 0) {

@@ -25,6 +25,15 @@ __device__ __forceinline__ double* upd_base(double* upd, const DevSym& sy, int W
     const int lw = lg2(W);
     return upd + sy.sec_base[lw] + (long long)(s / W) * sy.sec_size[lw] * W + (s % W);
 }
+// same for the packed U rows (usec_* sections): add (f_uoff + e) * W for an entry
+__device__ __forceinline__ double* u_base(double* U, const DevSym& sy, int W, int s) {
+    const int lw = lg2(W);
+    return U + sy.usec_base[lw] + (long long)(s / W) * sy.usec_size[lw] * W + (s % W);
+}
+__device__ __forceinline__ const double* u_base(const double* U, const DevSym& sy, int W, int s) {
+    const int lw = lg2(W);
+    return U + sy.usec_base[lw] + (long long)(s / W) * sy.usec_size[lw] * W + (s % W);
+}
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
 __device__ __forceinline__ long long urow_off(int p, int nf) {
@@ -63,6 +72,7 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
         fd.ea0 = sy.f_eaptr[f]; fd.ea1 = sy.f_eaptr[f + 1];
         fd.child0 = fd.child1 = 0;
         fd.wout = S < 32 ? S : 32;
+        fd.flags = fd.wout << 8;
         fd.uoff = sy.f_uoff[f]; fd.updoff = sy.f_updoff[f];
     }
     const int nf = fd.nf, k = fd.k, u = nf - k;
@@ -277,12 +287,13 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
     if (!act) return;
     if (bad && e0 == 0) status[s] = -3;
     if (weakp && sy.weak) sy.weak[s] = 1;
-    double* __restrict__ Uf = U + fd.uoff * S + s;
+    const int Wu = (fd.flags >> 8) & 0xff;      // tile width of the back-solve launch that reads these rows
+    double* __restrict__ Uf = u_base(U, sy, Wu, s) + fd.uoff * Wu;
     for (int p = ec; p < k; p += TC) {
-        double* Urow = Uf + urow_off(p, nf) * S;
+        double* Urow = Uf + urow_off(p, nf) * Wu;
         for (int j = p + er; j <= nf; j += TR) {
             const double v = Fl[(p + j * nf) * TS];
-            Urow[wide(j - p, S)] = (j == p) ? 1.0 / v : v;
+            Urow[(unsigned)((j - p) * Wu)] = (j == p) ? 1.0 / v : v;
         }
     }
     const int Wo = fd.wout;                     // the parent's tile width
@@ -411,13 +422,14 @@ mf_factor_sym_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doubl
     }
     if (!act) return;
     if (bad && e0 == 0) status[s] = -3;
-    double* __restrict__ Uf = U + fd.uoff * S + s;
+    const int Wu = (fd.flags >> 8) & 0xff;
+    double* __restrict__ Uf = u_base(U, sy, Wu, s) + fd.uoff * Wu;
     for (int p = ec; p < k; p += TC) {
-        double* Urow = Uf + urow_off(p, nf) * S;
+        double* Urow = Uf + urow_off(p, nf) * Wu;
         const double* colp = Fl + (sym_col(p, nf) - p) * TS;
         for (int j = p + er; j <= nf; j += TR) {
             const double v = (j < nf) ? colp[j * TS] : Rl[p * TS];
-            Urow[wide(j - p, S)] = (j == p) ? 1.0 / v : v;
+            Urow[(unsigned)((j - p) * Wu)] = (j == p) ? 1.0 / v : v;
         }
     }
     const int Wo = fd.wout;
@@ -613,7 +625,8 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
         for (int i = 0; i < MAXNF; ++i) col[q][i] = (c <= nf && i < nf) ? Fl[(i + c * nf) * 32] : 0.0;
     }
     bool bad = false, weakp = false;
-    double* __restrict__ Uf = U + fd.uoff * S + s;
+    const int Wu = (fd.flags >> 8) & 0xff;      // 32 when the register back-solve reads these rows
+    double* __restrict__ Uf = u_base(U, sy, Wu, s) + fd.uoff * Wu;
 #pragma unroll
     for (int p = 0; p < MAXNF; ++p) {
         if (p >= k) break;
@@ -634,14 +647,14 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
         const double piv = b[p * 32];
         if (piv == 0.0 || !isfinite(piv)) bad = true;
         const double inv = 1.0 / piv;
-        double* Urow = Uf + urow_off(p, nf) * S;
+        double* Urow = Uf + urow_off(p, nf) * Wu;
         double m[NC];                                   // multiplier of each owned column, 0 for columns not updated
 #pragma unroll
         for (int q = 0; q < NC; ++q) {
             const int c = e0 + q * TE;
             const double upc = col[q][p];               // U[p, c]
             const bool in = c >= p && c <= nf;
-            if (act && in) Urow[wide(c - p, S)] = (c == p) ? inv : upc;
+            if (act && in) Urow[(unsigned)((c - p) * Wu)] = (c == p) ? inv : upc;
             m[q] = (in && c > p) ? inv * upc : 0.0;
         }
 #pragma unroll
@@ -742,14 +755,14 @@ mf_backsolve_single(DevSym sy, const int* __restrict__ fronts, const double* __r
     const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
     double* xs = sh;              // nf entries: x of the front rows (pivots filled in as they are solved)
     double* Us = sh + nf;         // packed rows of the current block
-    const double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
+    const double* __restrict__ Uf = u_base(U, sy, 1, s) + sy.f_uoff[f];      // section W = 1: contiguous per scenario
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
     for (int j = k + threadIdx.x; j < nf; j += blockDim.x) xs[j] = x[wide(rows[j], S) + s];
     for (int p1 = k; p1 > 0; p1 -= bs_rows) {       // bs_rows <= 32: one lane of warp 0 per row of the block
         const int p0 = max(0, p1 - bs_rows);
         const long long base = urow_off(p0, nf);
         const int cnt = (int)(urow_off(p1, nf) - base);
-        for (int e = threadIdx.x; e < cnt; e += blockDim.x) Us[e] = Uf[(base + e) * S];
+        for (int e = threadIdx.x; e < cnt; e += blockDim.x) Us[e] = Uf[base + e];
         __syncthreads();
         // rows p0..p1-1: t_p = y_p - sum_{j >= p1} U[p,j] x_j
         for (int p = p0 + warp; p < p1; p += nwarps) {
@@ -798,8 +811,8 @@ mf_backsolve_tile_kernel(DevSym sy, const int* __restrict__ fronts, const double
     const int usz = (int)urow_off(k, nf);
     double* xs = sh + sl;                 // xs[j * TS]
     double* Us = sh + nf * TS + sl;       // Us[e * TS], packed rows
-    const double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
-    for (int q = e; q < usz; q += TE) Us[q * TS] = Uf[wide(q, S)];
+    const double* __restrict__ Uf = u_base(U, sy, TS, s) + sy.f_uoff[f] * TS;   // section W = TS: one contiguous run
+    for (int q = e; q < usz; q += TE) Us[q * TS] = Uf[(unsigned)(q * TS)];
     for (int j = k + e; j < nf; j += TE) xs[j * TS] = x[wide(rows[j], S) + s];
     __syncthreads();
     for (int p = e; p < k; p += TE) {
@@ -835,18 +848,18 @@ mf_backsolve_reg_kernel(DevSym sy, const int* __restrict__ fronts, int count, co
     const int f = fronts[item];
     const int nf = sy.f_nf[f], k = sy.f_k[f];
     const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
-    const double* __restrict__ Uf = U + sy.f_uoff[f] * S + s;
+    const double* __restrict__ Uf = u_base(U, sy, 32, s) + sy.f_uoff[f] * 32;    // section W = 32
     double xv[MAXNF];
 #pragma unroll
     for (int j = 0; j < MAXNF; ++j) xv[j] = (j >= k && j < nf) ? x[wide(rows[j], S) + s] : 0.0;
 #pragma unroll
     for (int p = MAXNF - 1; p >= 0; --p) {
         if (p < k) {
-            const double* __restrict__ Urow = Uf + urow_off(p, nf) * S;
-            double acc = Urow[wide(nf - p, S)];
+            const double* __restrict__ Urow = Uf + urow_off(p, nf) * 32;
+            double acc = Urow[(nf - p) * 32];
 #pragma unroll
             for (int j = p + 1; j < MAXNF; ++j)
-                if (j < nf) acc -= Urow[wide(j - p, S)] * xv[j];
+                if (j < nf) acc -= Urow[(j - p) * 32] * xv[j];
             xv[p] = acc * Urow[0];
         }
     }
@@ -1105,7 +1118,10 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
     JGB_CUDA(cudaFuncSetAttribute(mf_factor_dense_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     dev.upd_size = sym.upd_size;
     dev.child_desc = d_child_desc.p;
-    for (int q = 0; q < 6; ++q) { dev.sec_base[q] = 0; dev.sec_size[q] = sym.upd_size; }
+    for (int q = 0; q < 6; ++q) {
+        dev.sec_base[q] = 0; dev.sec_size[q] = sym.upd_size;
+        dev.usec_base[q] = 0; dev.usec_size[q] = sym.u_size;
+    }
     dev.weak = nullptr;
     dev.growth = 1e300;
     JGB_CUDA(cudaFuncSetAttribute(mf_backsolve_single, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -1292,112 +1308,6 @@ void MfSolver::plan(int S) {
             i = j;
         }
     }
-    {
-        // Tile width of every front's launch, and with it the section of the update storage each block goes to: the
-        // block of front f is written at the width its PARENT reads with (see DevSym).
-        const int F = sym.nfronts;
-        const int wmax = S < 32 ? S : 32;
-        std::vector<int> ts_of(F, wmax);
-        std::vector<char> lower(F, 0);
-        for (const FactorLaunch& fl : fplan)
-            for (int q = fl.begin; q < fl.begin + fl.count; ++q) {
-                const int f = plan_fronts[q];
-                ts_of[f] = fl.bulk ? wmax : fl.ts;
-                if ((fl.sym || fl.dense) && !fl.bulk) lower[f] = 1;
-            }
-        std::vector<int> wout(F, wmax);
-        std::vector<long long> off(F, 0), secsz(6, 0);
-        for (int f = 0; f < F; ++f) {
-            const int par = sym.f_parent[f];
-            wout[f] = par < 0 ? wmax : ts_of[par];
-            const long long u = sym.f_nf[f] - sym.f_k[f];
-            off[f] = secsz[lg2(wout[f])];
-            secsz[lg2(wout[f])] += u * (u + 1);
-        }
-        long long base = 0;
-        for (int q = 0; q < 6; ++q) {
-            dev.sec_base[q] = base * S;
-            dev.sec_size[q] = secsz[q];
-            base += secsz[q];
-            if (secsz[q] >= (1LL << 31) / 32) throw std::runtime_error("update-storage section exceeds the 32-bit element offsets");
-        }
-        if (!tplan.empty()) {          // task blobs: update-storage offsets and root tile widths of this layout
-            std::vector<int> blob(task_plan.blob);
-            for (size_t q = 0; q < task_plan.off_pos.size(); ++q) {
-                const long long o = off[task_plan.off_front[q]];
-                blob[task_plan.off_pos[q]] = (int)(o & 0xffffffffLL);
-                blob[task_plan.off_pos[q] + 1] = (int)(o >> 32);
-            }
-            for (size_t q = 0; q < task_plan.wout_pos.size(); ++q) blob[task_plan.wout_pos[q]] = wout[task_plan.wout_front[q]];
-            d_task_blob.alloc(blob.size());
-            d_task_desc.alloc(task_plan.descs.size() / 2);
-            JGB_CUDA(cudaMemcpy(d_task_blob.p, blob.data(), blob.size() * sizeof(int), cudaMemcpyHostToDevice));
-            JGB_CUDA(cudaMemcpy(d_task_desc.p, task_plan.descs.data(), task_plan.descs.size() * sizeof(int),
-                                cudaMemcpyHostToDevice));
-        }
-        // gather lists with the source offsets of this layout: a pair's source is (child block offset + element)
-        auto remap = [&](const std::vector<int>& eaptr, const std::vector<int>& roundptr, const std::vector<int>& pairs,
-                         DevBuf<int>& out) {
-            std::vector<int> np(pairs);
-            for (int f = 0; f < F; ++f) {
-                const int c0 = sym.f_childptr[f], c1 = sym.f_childptr[f + 1];
-                if (c0 == c1) continue;
-                for (int t = roundptr[eaptr[f]]; t < roundptr[eaptr[f + 1]]; ++t) {
-                    const long long src = pairs[2 * t + 1];
-                    int lo = c0, hi = c1 - 1;               // children ascend in index and in f_updoff
-                    while (lo < hi) {
-                        const int mid = (lo + hi + 1) / 2;
-                        if (sym.f_updoff[sym.f_children[mid]] <= src) lo = mid; else hi = mid - 1;
-                    }
-                    const int c = sym.f_children[lo];
-                    np[2 * t + 1] = (int)(off[c] + (src - sym.f_updoff[c]));
-                }
-            }
-            out.alloc(np.size());
-            if (!np.empty()) JGB_CUDA(cudaMemcpy(out.p, np.data(), np.size() * sizeof(int), cudaMemcpyHostToDevice));
-        };
-        remap(sym.f_eaptr, sym.ea_roundptr, sym.ea_pair, d_plan_pair);
-        dev.ea_pair = reinterpret_cast<const int2*>(d_plan_pair.p);
-        if (symmetric) {
-            remap(sym.f_eaptr_sym, sym.ea_roundptr_sym, sym.ea_pair_sym, d_plan_pair_s);
-            dev.ea_pair_s = reinterpret_cast<const int2*>(d_plan_pair_s.p);
-        }
-        {
-            std::vector<ChildDesc> cds(sym.f_children.size());
-            for (size_t q = 0; q < cds.size(); ++q) {
-                const int c = sym.f_children[q];
-                cds[q].uc = sym.f_nf[c] - sym.f_k[c];
-                cds[q].relptr = sym.f_relptr[c];
-                cds[q].updoff = off[c];
-            }
-            d_plan_child.alloc(cds.size());
-            if (!cds.empty()) JGB_CUDA(cudaMemcpy(d_plan_child.p, cds.data(), cds.size() * sizeof(ChildDesc), cudaMemcpyHostToDevice));
-            dev.child_desc = d_plan_child.p;
-        }
-        // per-front descriptors in launch order. Fronts factored on packed lower triangles (LDL^T kernels) take the
-        // symmetric gather lists, and a front whose parent is such a front writes only the lower triangle of its block.
-        std::vector<FrontDesc> descs(plan_fronts.size());
-        for (size_t q = 0; q < descs.size(); ++q) {
-            const int f = plan_fronts[q];
-            FrontDesc& d = descs[q];
-            d.f = f; d.nf = sym.f_nf[f]; d.k = sym.f_k[f]; d.rowptr = sym.f_rowptr[f];
-            d.asm0 = sym.f_asmptr[f]; d.asm1 = sym.f_asmptr[f + 1];
-            d.child0 = sym.f_childptr[f]; d.child1 = sym.f_childptr[f + 1];
-            if (lower[f]) { d.ea0 = sym.f_eaptr_sym[f]; d.ea1 = sym.f_eaptr_sym[f + 1]; }
-            else { d.ea0 = sym.f_eaptr[f]; d.ea1 = sym.f_eaptr[f + 1]; }
-            const int par = sym.f_parent[f];
-            d.flags = (par >= 0 && lower[par]) ? 1 : 0;
-            d.wout = wout[f];
-            d.uoff = sym.f_uoff[f]; d.updoff = off[f];
-        }
-        d_plan_desc.alloc(descs.size());
-        d_plan_fronts.alloc(plan_fronts.size());
-        if (!descs.empty()) {
-            JGB_CUDA(cudaMemcpy(d_plan_desc.p, descs.data(), descs.size() * sizeof(FrontDesc), cudaMemcpyHostToDevice));
-            JGB_CUDA(cudaMemcpy(d_plan_fronts.p, plan_fronts.data(), plan_fronts.size() * sizeof(int),
-                                cudaMemcpyHostToDevice));
-        }
-    }
     // back-solve: one launch per depth level; batch launches are additionally cut by front size so that the
     // scenario tile (shared-memory footprint of the staged U rows) matches the class
     static const std::vector<PlanRule> bs_rules = {{8, 32, 128}, {12, 32, 128}, {16, 32, 128}, {24, 16, 128},
@@ -1456,6 +1366,142 @@ void MfSolver::plan(int S) {
             sl.smem = smem;
             splan.push_back(sl);
             i = j;
+        }
+    }
+    {
+        // Tile width of every front's launch, and with it the section of the update storage each block goes to: the
+        // block of front f is written at the width its PARENT reads with (see DevSym).
+        const int F = sym.nfronts;
+        const int wmax = S < 32 ? S : 32;
+        std::vector<int> ts_of(F, wmax);
+        std::vector<char> lower(F, 0);
+        for (const FactorLaunch& fl : fplan)
+            for (int q = fl.begin; q < fl.begin + fl.count; ++q) {
+                const int f = plan_fronts[q];
+                ts_of[f] = fl.bulk ? wmax : fl.ts;
+                if ((fl.sym || fl.dense) && !fl.bulk) lower[f] = 1;
+            }
+        std::vector<int> wout(F, wmax);
+        std::vector<long long> off(F, 0), secsz(6, 0);
+        for (int f = 0; f < F; ++f) {
+            const int par = sym.f_parent[f];
+            wout[f] = par < 0 ? wmax : ts_of[par];
+            const long long u = sym.f_nf[f] - sym.f_k[f];
+            off[f] = secsz[lg2(wout[f])];
+            secsz[lg2(wout[f])] += u * (u + 1);
+        }
+        // packed U rows: section = tile width of the back-solve launch that reads the front's rows
+        std::vector<int> wu(F, wmax);
+        for (const SolveLaunch& sl : splan) {
+            const bool reg = !sl.blocked && sl.max_nf <= backsolve_reg_max() && S % 32 == 0;
+            const int w = sl.blocked ? 1 : reg ? 32 : sl.ts;
+            for (int q = sl.begin; q < sl.begin + sl.count; ++q) wu[sym.depth_fronts[q]] = std::min(w, wmax);
+        }
+        std::vector<long long> uoff(F, 0), usecsz(6, 0);
+        for (int f = 0; f < F; ++f) {
+            uoff[f] = usecsz[lg2(wu[f])];
+            usecsz[lg2(wu[f])] += sym.f_uoff.size() > (size_t)f + 1 ? sym.f_uoff[f + 1] - sym.f_uoff[f] : sym.u_size - sym.f_uoff[f];
+        }
+        {
+            long long ub = 0;
+            for (int q = 0; q < 6; ++q) {
+                dev.usec_base[q] = ub * S;
+                dev.usec_size[q] = usecsz[q];
+                ub += usecsz[q];
+                if (usecsz[q] >= (1LL << 31) / 32) throw std::runtime_error("packed-U section exceeds the 32-bit element offsets");
+            }
+            d_plan_uoff.alloc(F);
+            if (F) JGB_CUDA(cudaMemcpy(d_plan_uoff.p, uoff.data(), (size_t)F * sizeof(long long), cudaMemcpyHostToDevice));
+            dev.f_uoff = d_plan_uoff.p;
+        }
+        long long base = 0;
+        for (int q = 0; q < 6; ++q) {
+            dev.sec_base[q] = base * S;
+            dev.sec_size[q] = secsz[q];
+            base += secsz[q];
+            if (secsz[q] >= (1LL << 31) / 32) throw std::runtime_error("update-storage section exceeds the 32-bit element offsets");
+        }
+        if (!tplan.empty()) {          // task blobs: update-storage offsets and root tile widths of this layout
+            std::vector<int> blob(task_plan.blob);
+            for (size_t q = 0; q < task_plan.off_pos.size(); ++q) {
+                const long long o = off[task_plan.off_front[q]];
+                blob[task_plan.off_pos[q]] = (int)(o & 0xffffffffLL);
+                blob[task_plan.off_pos[q] + 1] = (int)(o >> 32);
+            }
+            for (size_t q = 0; q < task_plan.wout_pos.size(); ++q) blob[task_plan.wout_pos[q]] = wout[task_plan.wout_front[q]];
+            for (size_t q = 0; q < task_plan.uoff_pos.size(); ++q) {
+                const int f = task_plan.uoff_front[q];
+                if (wu[f] != 32) throw std::logic_error("task front outside the register back-solve class");
+                blob[task_plan.uoff_pos[q]] = (int)(uoff[f] & 0xffffffffLL);
+                blob[task_plan.uoff_pos[q] + 1] = (int)(uoff[f] >> 32);
+            }
+            d_task_blob.alloc(blob.size());
+            d_task_desc.alloc(task_plan.descs.size() / 2);
+            JGB_CUDA(cudaMemcpy(d_task_blob.p, blob.data(), blob.size() * sizeof(int), cudaMemcpyHostToDevice));
+            JGB_CUDA(cudaMemcpy(d_task_desc.p, task_plan.descs.data(), task_plan.descs.size() * sizeof(int),
+                                cudaMemcpyHostToDevice));
+        }
+        // gather lists with the source offsets of this layout: a pair's source is (child block offset + element)
+        auto remap = [&](const std::vector<int>& eaptr, const std::vector<int>& roundptr, const std::vector<int>& pairs,
+                         DevBuf<int>& out) {
+            std::vector<int> np(pairs);
+            for (int f = 0; f < F; ++f) {
+                const int c0 = sym.f_childptr[f], c1 = sym.f_childptr[f + 1];
+                if (c0 == c1) continue;
+                for (int t = roundptr[eaptr[f]]; t < roundptr[eaptr[f + 1]]; ++t) {
+                    const long long src = pairs[2 * t + 1];
+                    int lo = c0, hi = c1 - 1;               // children ascend in index and in f_updoff
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) / 2;
+                        if (sym.f_updoff[sym.f_children[mid]] <= src) lo = mid; else hi = mid - 1;
+                    }
+                    const int c = sym.f_children[lo];
+                    np[2 * t + 1] = (int)(off[c] + (src - sym.f_updoff[c]));
+                }
+            }
+            out.alloc(np.size());
+            if (!np.empty()) JGB_CUDA(cudaMemcpy(out.p, np.data(), np.size() * sizeof(int), cudaMemcpyHostToDevice));
+        };
+        remap(sym.f_eaptr, sym.ea_roundptr, sym.ea_pair, d_plan_pair);
+        dev.ea_pair = reinterpret_cast<const int2*>(d_plan_pair.p);
+        if (symmetric) {
+            remap(sym.f_eaptr_sym, sym.ea_roundptr_sym, sym.ea_pair_sym, d_plan_pair_s);
+            dev.ea_pair_s = reinterpret_cast<const int2*>(d_plan_pair_s.p);
+        }
+        {
+            std::vector<ChildDesc> cds(sym.f_children.size());
+            for (size_t q = 0; q < cds.size(); ++q) {
+                const int c = sym.f_children[q];
+                cds[q].uc = sym.f_nf[c] - sym.f_k[c];
+                cds[q].relptr = sym.f_relptr[c];
+                cds[q].updoff = off[c];
+            }
+            d_plan_child.alloc(cds.size());
+            if (!cds.empty()) JGB_CUDA(cudaMemcpy(d_plan_child.p, cds.data(), cds.size() * sizeof(ChildDesc), cudaMemcpyHostToDevice));
+            dev.child_desc = d_plan_child.p;
+        }
+        // per-front descriptors in launch order. Fronts factored on packed lower triangles (LDL^T kernels) take the
+        // symmetric gather lists, and a front whose parent is such a front writes only the lower triangle of its block.
+        std::vector<FrontDesc> descs(plan_fronts.size());
+        for (size_t q = 0; q < descs.size(); ++q) {
+            const int f = plan_fronts[q];
+            FrontDesc& d = descs[q];
+            d.f = f; d.nf = sym.f_nf[f]; d.k = sym.f_k[f]; d.rowptr = sym.f_rowptr[f];
+            d.asm0 = sym.f_asmptr[f]; d.asm1 = sym.f_asmptr[f + 1];
+            d.child0 = sym.f_childptr[f]; d.child1 = sym.f_childptr[f + 1];
+            if (lower[f]) { d.ea0 = sym.f_eaptr_sym[f]; d.ea1 = sym.f_eaptr_sym[f + 1]; }
+            else { d.ea0 = sym.f_eaptr[f]; d.ea1 = sym.f_eaptr[f + 1]; }
+            const int par = sym.f_parent[f];
+            d.flags = ((par >= 0 && lower[par]) ? 1 : 0) | (wu[f] << 8);
+            d.wout = wout[f];
+            d.uoff = uoff[f]; d.updoff = off[f];
+        }
+        d_plan_desc.alloc(descs.size());
+        d_plan_fronts.alloc(plan_fronts.size());
+        if (!descs.empty()) {
+            JGB_CUDA(cudaMemcpy(d_plan_desc.p, descs.data(), descs.size() * sizeof(FrontDesc), cudaMemcpyHostToDevice));
+            JGB_CUDA(cudaMemcpy(d_plan_fronts.p, plan_fronts.data(), plan_fronts.size() * sizeof(int),
+                                cudaMemcpyHostToDevice));
         }
     }
     d_U.alloc((size_t)sym.u_size * S);

@@ -25,6 +25,9 @@ struct DevSym {
     // writes its own block as contiguous runs: element e of scenario s of a block at offset `off` of section W sits at
     //   sec_base[lw] + ((s / W) * sec_size[lw] + off + e) * W + s % W          (sec_size in elements per scenario)
     long long sec_base[6], sec_size[6];
+    // The packed U rows are sectioned the same way, by the tile width of the back-solve launch that READS them:
+    // entry e of scenario s of a front whose rows start at f_uoff sits at usec_base[lw] + ((s / W) * usec_size[lw] + f_uoff + e) * W + s % W
+    long long usec_base[6], usec_size[6];
     const struct ChildDesc* child_desc;
     // pivot guard (LU without pivoting): a multiplier |F[i,p] / F[p,p]| above `growth` marks the scenario in weak[] (nullable);
     // the caller then refines the solution of that scenario with one residual step
@@ -37,8 +40,10 @@ struct __align__(16) FrontDesc {
     int f, nf, k, rowptr;
     int asm0, asm1, child0, child1;
     int ea0, ea1;          // rounds of the extend-add gather (symmetric lists when the solver is symmetric)
-    int flags, wout;       // flags bit 0: the parent reads only the lower triangle + rhs of this front's update block;
-                           // wout: tile width of the section this front's block is written to (the parent's TS)
+    int flags, wout;       // flags bit 0: the parent reads only the lower triangle + rhs of this front's update block,
+                           // bits 8..15: tile width of the section this front's packed U rows are written to (the
+                           // back-solve launch's TS); wout: tile width of the section its update block is written to
+                           // (the parent's TS)
     long long uoff, updoff;
 };
 
@@ -113,6 +118,7 @@ class MfSolver {
     std::vector<int> plan_levelptr, plan_fronts;   // level schedule of the fronts left to fplan
     DevBuf<int> d_task_blob, d_plan_fronts, d_plan_pair, d_plan_pair_s;
     DevBuf<ChildDesc> d_plan_child;
+    DevBuf<long long> d_plan_uoff;
     DevBuf<int2> d_task_desc;
     DevBuf<FrontDesc> d_plan_desc;
     int planned_S = -1;

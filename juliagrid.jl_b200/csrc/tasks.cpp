@@ -207,6 +207,8 @@ void partition_tasks(const Symbolic& sym, const TaskOptions& opt, TaskPlan& out)
             rec[6] = (int)(sym.f_uoff[f] & 0xffffffffLL); rec[7] = (int)(sym.f_uoff[f] >> 32);
             rec[8] = (int)(sym.f_updoff[f] & 0xffffffffLL); rec[9] = (int)(sym.f_updoff[f] >> 32);
             rec[10] = 32;
+            out.uoff_pos.push_back((int)(rec0 + q * kTaskRec + 6));
+            out.uoff_front.push_back(f);
             out.off_pos.push_back((int)(rec0 + q * kTaskRec + 8));
             out.off_front.push_back(f);
             out.wout_pos.push_back((int)(rec0 + q * kTaskRec + 10));

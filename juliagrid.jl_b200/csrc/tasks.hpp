@@ -42,7 +42,7 @@ struct TaskPlan {
     // places in `blob` that hold an update-storage offset (lo word; hi word follows) or a tile width, with the front they
     // refer to: MfSolver::plan patches them once the layout of the update storage is known (the blob as built here
     // addresses the plain layout of Symbolic::f_updoff at tile width 32, which is what the host replay walks)
-    std::vector<int> off_pos, off_front, wout_pos, wout_front;
+    std::vector<int> off_pos, off_front, wout_pos, wout_front, uoff_pos, uoff_front;
     int task_fronts = 0, task_count = 0;
     long long upd_on_chip = 0;          // update-block elements per scenario that never leave shared memory
 };
