@@ -158,6 +158,7 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
     }
     bool bad = false, weakp = false;
     const int colstride = nf * TS;
+
     // Blocked right-looking elimination, panels of B pivots:
     //  (a) panel: rank-1 steps restricted to the panel columns (one barrier each, a handful of multiply-adds per
     //      row), the multipliers l_i = F[i,p] / F[p,p] overwrite column p (L is not an output);
@@ -188,7 +189,7 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
             for (int i = p + 1 + e0; i < nf; i += TE) {
                 double* rowi = pan + i * TS;
                 const double li = rowi[(p - p0) * colstride] * inv;
-                if (fabs(li) > sy.growth) weakp = true;
+
                 rowi[(p - p0) * colstride] = li;
                 for (int j = p + 1; j < pe; ++j) rowi[(j - p0) * colstride] -= li * pan[(p + (j - p0) * nf) * TS];
             }
@@ -286,16 +287,20 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
     }
     if (!act) return;
     if (bad && e0 == 0) status[s] = -3;
-    if (weakp && sy.weak) sy.weak[s] = 1;
     const int Wu = (fd.flags >> 8) & 0xff;      // tile width of the back-solve launch that reads these rows
     double* __restrict__ Uf = u_base(U, sy, Wu, s) + fd.uoff * Wu;
+    // pivot guard, evaluated where the U rows are written out (off the barrier-separated panel steps): an entry of row p
+    // more than `growth` times its pivot — the multiplier of the transposed elimination — marks the scenario
     for (int p = ec; p < k; p += TC) {
         double* Urow = Uf + urow_off(p, nf) * Wu;
+        const double lim = sy.growth * fabs(Fl[(p + p * nf) * TS]);
         for (int j = p + er; j <= nf; j += TR) {
             const double v = Fl[(p + j * nf) * TS];
+            if (j < nf && fabs(v) > lim) weakp = true;
             Urow[(unsigned)((j - p) * Wu)] = (j == p) ? 1.0 / v : v;
         }
     }
+    if (weakp && sy.weak) sy.weak[s] = 1;
     const int Wo = fd.wout;                     // the parent's tile width
     double* __restrict__ Cf = upd_base(upd, sy, Wo, s) + fd.updoff * Wo;
     for (int j = ec; j <= u; j += TC) {
@@ -632,18 +637,12 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
         if (p >= k) break;
         double* b = bc + (p & 1) * (MAXNF * 32) + sl;
         if (e0 == p % TE) {
-            // the warp that owns the pivot column publishes it and, while it holds it in registers, watches the pivot
-            // guard: largest entry below the pivot against growth * |pivot| (one compare per entry, this warp only)
-            double mx = 0.0;
 #pragma unroll
             for (int i = p; i < MAXNF; ++i)
-                if (i < nf) {
-                    b[i * 32] = col[p / TE][i];
-                    if (i > p) mx = fmax(mx, fabs(col[p / TE][i]));
-                }
-            if (mx > sy.growth * fabs(col[p / TE][p])) weakp = true;
+                if (i < nf) b[i * 32] = col[p / TE][i];
         }
         __syncthreads();
+
         const double piv = b[p * 32];
         if (piv == 0.0 || !isfinite(piv)) bad = true;
         const double inv = 1.0 / piv;
@@ -656,6 +655,7 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
             const bool in = c >= p && c <= nf;
             if (act && in) Urow[(unsigned)((c - p) * Wu)] = (c == p) ? inv : upc;
             m[q] = (in && c > p) ? inv * upc : 0.0;
+            if (c < nf && fabs(m[q]) > sy.growth) weakp = true;      // pivot guard: row multiplier U[p,c] / U[p,p]
         }
 #pragma unroll
         for (int i = p + 1; i < MAXNF; ++i) {
