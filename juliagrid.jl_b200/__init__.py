@@ -9,7 +9,8 @@ from .ac_power_flow import (AcPowerFlow, newton_raphson, mismatch, solve, power_
                             set_voltage, update_branch, power_device, newtonRaphson, powerFlow, setInitialPoint, updateBranch,
                             generator_power, reactive_limit, adjust_angle, generatorPower, reactiveLimit, adjustAngle)
 from .measurement import (Measurement, measurement, power, add_voltmeter, add_ammeter, add_wattmeter,  # noqa: F401
-                          add_varmeter, add_pmu, ac_wls, WlsTables)
+                          add_varmeter, add_pmu, ac_wls, WlsTables, load_measurement, measurement_from_arrays,
+                          measurement_to_arrays)
 from .ac_state_estimation import (AcStateEstimation, gauss_newton, increment, solve_se, state_estimation,  # noqa: F401
                                   set_mean, set_voltage_se, gaussNewton, stateEstimation, chi_test,
                                   residual_test, ChiTest, ResidualTest, chiTest, residualTest, update_voltmeter,

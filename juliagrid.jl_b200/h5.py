@@ -238,6 +238,8 @@ class H5File:
             return np.dtype(("<i" if signed else "<u") + str(size))
         if cls == 1:
             return np.dtype("<f" + str(size))
+        if cls == 4:          # bitfield: how HDF5.jl stores Julia Bool vectors (measurement layouts)
+            return np.dtype("<u" + str(size))
         return None
 
     def _dims(self, body: int):

@@ -58,6 +58,89 @@ def measurement(system: PowerSystem) -> Measurement:
     return Measurement(system)
 
 
+_H5_LAYOUT = {      # HDF5 group -> (device key, value group(s), layout flags), src/measurement/load.jl:190-273
+    "voltmeter": ("volt", {"magnitude": ("mean", "variance", "status")}, ()),
+    "ammeter": ("amp", {"magnitude": ("mean", "variance", "status")}, ("from", "square")),
+    "wattmeter": ("watt", {"active": ("mean", "variance", "status")}, ("bus", "from")),
+    "varmeter": ("var", {"reactive": ("mean", "variance", "status")}, ("bus", "from")),
+    "pmu": ("pmu", {"magnitude": ("mag_mean", "mag_variance", "mag_status"),
+                    "angle": ("ang_mean", "ang_variance", "ang_status")},
+            ("bus", "from", "polar", "square", "correlated")),
+}
+
+
+def measurement_from_arrays(system: PowerSystem, data: dict) -> Measurement:
+    """measurement(system, "file.h5") (src/measurement/load.jl:31-273) from the file's datasets keyed by their HDF5 path
+    ("wattmeter/active/mean", "pmu/layout/polar", ...): positional 1-based bus / branch indices, per-unit / radian
+    values, a scalar dataset stands for a constant vector. Labels are not kept (the mirror addresses meters by position)."""
+    mon = Measurement(system)
+    for group, (dev, values, flags) in _H5_LAYOUT.items():
+        key = group + "/layout/index"
+        if key not in data:
+            continue
+        index = np.atleast_1d(np.asarray(data[key])).astype(np.int64) - 1
+        count = len(index)
+
+        def vec(path, dtype):
+            v = np.asarray(data[path])
+            if v.ndim == 0 or (v.size == 1 and count != 1):
+                return np.full(count, v.reshape(-1)[0], dtype=dtype)
+            return v.astype(dtype)
+
+        cols = {"index": index}
+        for vgroup, (kmean, kvar, kstat) in values.items():
+            cols[kmean] = vec(f"{group}/{vgroup}/mean", np.float64)
+            cols[kvar] = vec(f"{group}/{vgroup}/variance", np.float64)
+            cols[kstat] = vec(f"{group}/{vgroup}/status", np.int64)
+        for flag in flags:
+            cols["frm" if flag == "from" else flag] = vec(f"{group}/layout/{flag}", bool)
+        onbus = np.ones(count, dtype=bool) if dev == "volt" else cols.get("bus", np.zeros(count, dtype=bool))
+        limit = np.where(onbus, system.n, len(system.status))
+        if np.any(index < 0) or np.any(index >= limit):
+            raise ValueError(f"{group}: bus / branch index outside the power system")
+        mon._append(dev, **cols)
+    return mon
+
+
+def measurement_to_arrays(mon: Measurement) -> dict:
+    """The datasets `saveMeasurement` writes (src/measurement/save.jl:40-118), keyed by their HDF5 path: the inverse of
+    `measurement_from_arrays` (1-based positional indices, `to` = not `from` for branch meters)."""
+    out = {}
+    for group, (dev, values, flags) in _H5_LAYOUT.items():
+        d = getattr(mon, dev)
+        if len(d["index"]) == 0:
+            continue
+        out[f"{group}/layout/index"] = d["index"] + 1
+        for vgroup, keys in values.items():
+            for name, k in zip(("mean", "variance", "status"), keys):
+                out[f"{group}/{vgroup}/{name}"] = d[k].copy()
+        for flag in flags:
+            out[f"{group}/layout/{flag}"] = d["frm" if flag == "from" else flag].copy()
+        if "from" in flags:
+            bus = d["bus"] if "bus" in d else np.zeros(len(d["index"]), dtype=bool)
+            out[f"{group}/layout/to"] = ~d["frm"] & ~bus
+    return out
+
+
+def load_measurement(system: PowerSystem, path: str) -> Measurement:
+    """measurement(system, path): JuliaGrid's HDF5 measurement files (`saveMeasurement`, src/measurement/save.jl) read with
+    the mirror's own pure-Python HDF5 reader; `.m` is not a measurement format (load.jl:49-51)."""
+    if not path.endswith(".h5"):
+        raise ValueError("The extension of the measurement file must be .h5")
+    from .h5 import H5File
+    f = H5File(path)
+    data = {}
+    for group, (_, values, flags) in _H5_LAYOUT.items():
+        if group not in f.keys("/"):
+            continue
+        names = [f"{group}/layout/index"] + [f"{group}/layout/{fl}" for fl in flags]
+        for vgroup in values:
+            names += [f"{group}/{vgroup}/{k}" for k in ("mean", "variance", "status")]
+        for nm in names:
+            data[nm] = f["/" + nm]
+    return measurement_from_arrays(system, data)
+
+
 def power(system: PowerSystem, vm, va) -> dict:
     """power!/current! values the generators consume (src/postprocessing/acAnalysis.jl:30-170, 672-723)."""
     mdl: AcModel = system.model or ac_model(system)

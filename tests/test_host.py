@@ -369,3 +369,38 @@ def test_task_partition_host_replay(case, monkeypatch):
             assert st[2] > 0.8 * st[6] or env          # the default caps put most fronts into tasks
         for k in env:
             monkeypatch.delenv(k)
+
+
+def test_measurement_file_layout_round_trip():
+    """measurement(system, "file.h5") (src/measurement/load.jl:31-273): the datasets of saveMeasurement's layout
+    (save.jl:40-118) rebuild the same Measurement, scalar datasets stand for constant vectors, the acWLS tables built
+    from the reloaded set are identical, and a non-HDF5 extension is refused like load.jl:49-51."""
+    ps, os_ = product_system("case14test"), oracle_system("case14test")
+    ps.model = jgb200.ac_model(ps)
+    o = onr.newton_raphson(os_)
+    assert onr.power_flow(o)
+    pw = jgb200.power(ps, o.vm, o.va)
+    mon = jgb200.measurement(ps)
+    jgb200.add_voltmeter(mon, o.vm)
+    jgb200.add_ammeter(mon, pw, square=True)
+    jgb200.add_wattmeter(mon, pw)
+    jgb200.add_varmeter(mon, pw)
+    jgb200.add_pmu(mon, pw, o.vm, o.va, buses=range(ps.n), branch=True, polar=False, correlated=True)
+    mon.watt["status"][5] = 0
+    data = jgb200.measurement_to_arrays(mon)
+    assert data["voltmeter/layout/index"].min() == 1
+    assert np.array_equal(data["pmu/layout/to"], ~mon.pmu["frm"] & ~mon.pmu["bus"])
+    data["voltmeter/magnitude/variance"] = np.float64(mon.volt["variance"][0])      # scalar dataset = constant vector
+    back = jgb200.measurement_from_arrays(ps, data)
+    for dev in ("volt", "amp", "watt", "var", "pmu"):
+        for k, v in getattr(mon, dev).items():
+            assert np.array_equal(getattr(back, dev)[k], v), (dev, k)
+    t0, t1 = jgb200.ac_wls(ps, mon), jgb200.ac_wls(ps, back)
+    for k in ("h_colptr", "h_rowval", "type", "index", "range", "mean", "w_nzval"):
+        assert np.array_equal(getattr(t0, k), getattr(t1, k)), k
+    with pytest.raises(ValueError):
+        jgb200.load_measurement(ps, "monitoring.m")
+    bad = dict(data)
+    bad["voltmeter/layout/index"] = data["voltmeter/layout/index"] + ps.n
+    with pytest.raises(ValueError):
+        jgb200.measurement_from_arrays(ps, bad)
