@@ -7,6 +7,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <string>
 
@@ -40,6 +41,32 @@ __device__ __forceinline__ long long urow_off(int p, int nf) {
     return (long long)p * (nf + 1) - (long long)p * (p - 1) / 2;
 }
 
+// ---- mbarrier / bulk-copy (TMA) helpers ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+
 // One CTA = one front x TS scenarios. Thread t: scenario lane sl = t % TS, entry lane e = t / TS,
 // entry lanes are arranged TR (rows) x TC (columns). Front F is column major, ld = nf, nf+1 columns,
 // element (r,c) of scenario lane sl at F[(r + c*nf) * TS + sl].  TS and the address space of F are compile-time
@@ -49,8 +76,9 @@ __global__ void __launch_bounds__(TS == 1 ? 512 : 256)
 mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __restrict__ descs,
                  const double* __restrict__ aval, const double* __restrict__ rhs, double* __restrict__ U,
                  double* __restrict__ upd, int S, int TR, const unsigned char* __restrict__ active,
-                 int* __restrict__ status, double* gwork, long long gstride, int ea_async) {
-    extern __shared__ double Fs[];
+                 int* __restrict__ status, double* gwork, long long gstride, int ea_async, StagedEa sg) {
+    extern __shared__ __align__(128) double Fs[];
+    __shared__ __align__(8) uint64_t ea_bar[2];
     const int sl = threadIdx.x % TS;
     double* Fl;     // this thread's scenario lane of the front: element (r,c) at Fl[(r + c*nf) * TS]
     if constexpr (GLOBAL_F) Fl = gwork + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * gstride + sl;
@@ -82,6 +110,31 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
     // the children's blocks live in the update-storage section of this launch's tile width (see DevSym)
     constexpr int W = TS;
     double* __restrict__ up = upd_base(upd, sy, TS, s);
+    // Staged extend-add (batches, TS >= 2): the children's blocks are contiguous runs of this tile's section, so one
+    // elected thread streams them through a two-stage ring behind the front with cp.async.bulk (chunks of one child,
+    // child order), completion on an mbarrier per stage; the first two chunks fly while the front is zeroed and the
+    // matrix entries are assembled. Destinations come from a list in source order (upd_dst), one coalesced read.
+    constexpr bool kCanStage = (TS >= 2) && !GLOBAL_F;
+    int nch = 0;
+    double* ring = nullptr;
+    const double* tile_src = nullptr;
+    if constexpr (kCanStage) {
+        if (sg.chunks) {
+            nch = fd.child1 - fd.child0;
+            ring = Fs + sg.ring_off;
+            tile_src = upd + sy.sec_base[lg2(TS)] + (long long)blockIdx.y * sy.sec_size[lg2(TS)] * TS;
+            if (threadIdx.x == 0 && nch > 0) {
+                mbar_init(&ea_bar[0], 1);
+                mbar_init(&ea_bar[1], 1);
+                for (int c = 0; c < 2 && c < nch; ++c) {
+                    const int2 cd = sg.chunks[fd.child0 + c];
+                    const uint32_t bytes = (uint32_t)cd.y * (TS * 8);
+                    mbar_expect_tx(&ea_bar[c], bytes);
+                    bulk_g2s(ring + (size_t)c * sg.ring_elems * TS, tile_src + (size_t)cd.x * TS, bytes, &ea_bar[c]);
+                }
+            }
+        }
+    }
     for (int pos = e0; pos < total; pos += TE) Fl[pos * TS] = 0.0;
     __syncthreads();
     // Round 0 of the extend-add (the first source of every destination — for the fronts at the top of the tree that is
@@ -90,7 +143,7 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
     // matrix entries are fetched into registers meanwhile and added once the copies have landed.
     bool async_r0 = false;
     if constexpr (!GLOBAL_F) {
-        if (ea_async && fd.ea1 > fd.ea0) {
+        if (ea_async && fd.ea1 > fd.ea0 && !sg.chunks) {
             async_r0 = true;
             if (act) {
                 const int t1 = sy.ea_roundptr[fd.ea0 + 1];
@@ -141,7 +194,36 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
         }
     }
     __syncthreads();
-    {
+    if (kCanStage && sg.chunks) {
+        if constexpr (kCanStage) {
+            for (int c = 0; c < nch; ++c) {
+                const int2 cd = sg.chunks[fd.child0 + c];
+                const int* __restrict__ dl = sg.upd_dst + sg.sec_cum + cd.x;
+                constexpr int NQ = 4;
+                int di[NQ];
+#pragma unroll
+                for (int q = 0; q < NQ; ++q) {
+                    const int e = e0 + q * TE;
+                    di[q] = (e < cd.y) ? dl[e] : -1;
+                }
+                mbar_wait(&ea_bar[c & 1], (c >> 1) & 1);
+                const double* rg = ring + (size_t)(c & 1) * sg.ring_elems * TS + sl;
+                if (act) {
+#pragma unroll
+                    for (int q = 0; q < NQ; ++q)
+                        if (di[q] >= 0) Fl[di[q] * TS] += rg[(e0 + q * TE) * TS];
+                    for (int e = e0 + NQ * TE; e < cd.y; e += TE) Fl[dl[e] * TS] += rg[e * TS];
+                }
+                __syncthreads();
+                if (threadIdx.x == 0 && c + 2 < nch) {
+                    const int2 nd = sg.chunks[fd.child0 + c + 2];
+                    const uint32_t bytes = (uint32_t)nd.y * (TS * 8);
+                    mbar_expect_tx(&ea_bar[c & 1], bytes);
+                    bulk_g2s(ring + (size_t)(c & 1) * sg.ring_elems * TS, tile_src + (size_t)nd.x * TS, bytes, &ea_bar[c & 1]);
+                }
+            }
+        }
+    } else {
         // extend-add of all children as a gather in rounds (child order per destination, so sums are deterministic)
         const int r1 = fd.ea1;
         for (int r = fd.ea0 + (async_r0 ? 1 : 0); r < r1; ++r) {      // rounds: distinct destinations inside a round
@@ -469,31 +551,6 @@ void launch_factor_sym(int ts, dim3 grid, int threads, size_t smem, cudaStream_t
 }
 
 // ---- TMA-staged variant for the many small fronts of a batch -------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst)),
-                 "l"(src), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile(
-            "{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-
 constexpr int kBulkMaxChildren = 32;   // children staged per group
 
 // One CTA = one front x one tile of 32 scenarios (lane = scenario), TE warps split the entries. The update blocks
@@ -687,7 +744,7 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
 template <bool GLOBAL_F>
 void launch_factor(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st, DevSym dev, const int* fronts,
                    const FrontDesc* descs, const double* aval, const double* rhs, double* U, double* upd, int S, int tr,
-                   const unsigned char* active, int* status, double* gwork, long long gstride) {
+                   const unsigned char* active, int* status, double* gwork, long long gstride, StagedEa sg = StagedEa{}) {
     // cp.async round 0 of the extend-add: measured on the 10k-bus Jacobian single case 509 -> 491 us per factorisation,
     // batch of 10 016 scenarios 43.6 -> 44.8 ms (the batch gather is not bound by loads in flight): single case only.
     // JGB_ASYNC_EA=0/1 forces it (tuning only).
@@ -696,7 +753,7 @@ void launch_factor(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st,
 #define JGB_CASE(T)                                                                                                  \
     case T:                                                                                                          \
         mf_factor_kernel<T, GLOBAL_F><<<grid, threads, smem, st>>>(dev, fronts, descs, aval, rhs, U, upd, S, tr,     \
-                                                                   active, status, gwork, gstride, ea_async);        \
+                                                                   active, status, gwork, gstride, ea_async, sg);    \
         break;
     switch (ts) {
         JGB_CASE(1) JGB_CASE(2) JGB_CASE(4) JGB_CASE(8) JGB_CASE(16) JGB_CASE(32)
@@ -746,11 +803,17 @@ constexpr int kBsRows = 32;
 // element stride S): strided reads, but only the few top-of-tree fronts of very large cases (e.g. 271 rows at 70k buses).
 __global__ void __launch_bounds__(512)
 mf_backsolve_single(DevSym sy, const int* __restrict__ fronts, const double* __restrict__ U,
-                    double* __restrict__ x, const unsigned char* __restrict__ active, int S, int bs_rows) {
+                    double* __restrict__ x, const unsigned char* __restrict__ active, int S, int bs_rows,
+                    const int* __restrict__ seqptr) {
     extern __shared__ double sh[];
     const int s = blockIdx.y;
     if (active && !active[s]) return;
-    const int f = fronts[blockIdx.x];
+    // sequence mode (seqptr): the CTA walks a chain of fronts from the last (closest to the root) to the first; x of a
+    // front's pivots is in global memory before the barrier that starts its child
+    const int d0 = seqptr ? seqptr[blockIdx.x] : blockIdx.x, d1 = seqptr ? seqptr[blockIdx.x + 1] : blockIdx.x + 1;
+    for (int di = d1 - 1; di >= d0; --di) {
+    if (di != d1 - 1) __syncthreads();
+    const int f = fronts[di];
     const int nf = sy.f_nf[f], k = sy.f_k[f];
     const int* __restrict__ rows = sy.f_rows + sy.f_rowptr[f];
     double* xs = sh;              // nf entries: x of the front rows (pivots filled in as they are solved)
@@ -790,6 +853,7 @@ mf_backsolve_single(DevSym sy, const int* __restrict__ fronts, const double* __r
         __syncthreads();
     }
     for (int p = threadIdx.x; p < k; p += blockDim.x) x[wide(rows[p], S) + s] = xs[p];
+    }
 }
 
 // Backward substitution, batch: one CTA per (front, tile of TS scenarios), TE = blockDim / TS lanes per scenario.
@@ -1116,6 +1180,7 @@ void MfSolver::setup(const Symbolic& s, cudaStream_t st, bool symmetric_matrix) 
 #undef X
     set_task_smem_attr();
     JGB_CUDA(cudaFuncSetAttribute(mf_factor_dense_sym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+    JGB_CUDA(cudaFuncSetAttribute(mf_factor_dense_lu_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     dev.upd_size = sym.upd_size;
     dev.child_desc = d_child_desc.p;
     for (int q = 0; q < 6; ++q) {
@@ -1192,6 +1257,8 @@ void MfSolver::plan(int S) {
                                                           {kMaxSymFront, 1, 1024}};
     const char* nb = getenv("JGB_NO_BULK");
     const bool bulk_enabled = !(nb && *nb == '1');
+    // JGB_STAGED_EA=0 falls back to the gather in rounds (A/B runs)
+    static const bool staged_enabled = !(getenv("JGB_STAGED_EA") && atoi(getenv("JGB_STAGED_EA")) == 0);
     const std::vector<PlanRule> rules = (S == 1) ? parse_rules("JGB_FPLAN_SINGLE", symmetric ? single_rules_sym : single_rules)
                                                  : parse_rules("JGB_FPLAN_BATCH", symmetric ? batch_rules_sym : batch_rules);
     // LDL^T fronts above dense_min rows take the one-scenario-per-CTA kernel with the FP64 tensor-core trailing update.
@@ -1204,6 +1271,23 @@ void MfSolver::plan(int S) {
     auto dense_ok = [&](int nf) {
         return symmetric && nf > dense_min && nf <= kMaxSymFront && dense_smem_doubles(nf) * sizeof(double) <= 220 * 1024;
     };
+    // LU twin (unsymmetric values): single case from 17 rows (the top of the tree is a chain of 45-70-row fronts, one CTA
+    // each: panel latency is the Newton step; measured 492 -> 368 us per factorisation with every front on it); batches keep
+    // the scenario-tile kernels. JGB_DENSE_LU_MIN = smallest front order that takes it, 0 = off (tuning only)
+    static const int dense_lu_env = getenv("JGB_DENSE_LU_MIN") ? atoi(getenv("JGB_DENSE_LU_MIN")) : -1;
+    static const int dense_lu_threads = getenv("JGB_DENSE_LU_THREADS") ? atoi(getenv("JGB_DENSE_LU_THREADS")) : 256;
+    const int dense_lu_min = dense_lu_env == 0 ? (1 << 30) : dense_lu_env > 0 ? dense_lu_env - 1 : (S == 1 ? 0 : (1 << 30));
+    auto dense_lu_ok = [&](int nf) {
+        return !symmetric && nf > dense_lu_min && dense_lu_smem_doubles(nf) * sizeof(double) <= 200 * 1024;
+    };
+    // dense LU launches of a single case gather their children through a ring of two 16 KB stages behind the front
+    auto stage_dense_lu = [&](FactorLaunch& fl) {
+        if (!staged_enabled || S != 1 || fl.smem + 2 * 16384 > 200 * 1024) return;
+        fl.staged = true;
+        fl.ring_elems = 2048;
+        fl.ring_off = (int)(fl.smem / 8);
+        fl.smem += 2 * 16384;
+    };
     auto cls0 = [&](int nf) { size_t c = 0; while (c < rules.size() && nf > rules[c].maxnf) ++c; return (int)c; };
     // dense fronts of a level are launched in buckets of similar order, so that the shared-memory footprint (and with
     // it the number of resident CTAs) follows the fronts of the bucket, not the largest front of the level
@@ -1211,17 +1295,99 @@ void MfSolver::plan(int S) {
     // 128-thread CTAs 34.3 ms; a single case pays for the extra launches — 1.76 -> 2.42 ms — and keeps one launch per level)
     static const int dense_bucket = getenv("JGB_DENSE_BUCKET") ? std::max(8, atoi(getenv("JGB_DENSE_BUCKET"))) : 32;
     static const int dense_small = getenv("JGB_DENSE_SMALL") ? atoi(getenv("JGB_DENSE_SMALL")) : 0;
-    auto cls = [&](int nf) { return dense_ok(nf) ? 1000 + (S == 1 ? 0 : (nf - 1) / dense_bucket) : cls0(nf); };
+    static const int dense_threads_single = getenv("JGB_DENSE_THREADS") ? atoi(getenv("JGB_DENSE_THREADS")) : 0;
+    auto cls = [&](int nf) {
+        if (dense_lu_ok(nf)) return 2000 + (S == 1 ? 0 : (nf - 1) / 16);
+        return dense_ok(nf) ? 1000 + (S == 1 ? 0 : (nf - 1) / dense_bucket) : cls0(nf);
+    };
     build_tasks(S, 0);
     // level schedule of the fronts the task launches leave over
     plan_levelptr.assign(1, 0);
     plan_fronts.clear();
-    for (int l = 0; l < sym.nlevels; ++l) {
-        for (int q = sym.levelptr[l]; q < sym.levelptr[l + 1]; ++q)
-            if (!in_task[sym.level_fronts[q]]) plan_fronts.push_back(sym.level_fronts[q]);
-        plan_levelptr.push_back((int)plan_fronts.size());
+    plan_seqptr.clear();
+    // Single case, every front on the dense LU kernel: chains at the narrow top of the tree (a front whose largest child
+    // sits one level below, on levels of at most seq_width fronts) become sequences that one CTA walks without leaving
+    // the kernel, and launches follow dependency slots — slot(sequence) = 1 + the largest slot among the sequences that
+    // hold children of its members — instead of tree levels. On the 10k-bus Jacobian the two chains of 11 fronts above
+    // level 9 collapse into one launch: 21 factor + 21 back-solve launches become 11 + 11. JGB_SEQ=0 turns it off.
+    static const int seq_env = getenv("JGB_SEQ") ? atoi(getenv("JGB_SEQ")) : 0;
+    seq_mode = (S == 1) && !symmetric && seq_env > 0 && tplan.empty();
+    for (int f = 0; f < sym.nfronts && seq_mode; ++f) seq_mode = dense_lu_ok(sym.f_nf[f]);
+    std::vector<int> slot_seqptr;          // per slot: range of sequences (indices into plan_seqptr)
+    if (seq_mode) {
+        const int F = sym.nfronts;
+        std::vector<int> lvl(F, 0), seq_of(F, -1);
+        std::vector<std::vector<int>> seqs;
+        for (int l = 0; l < sym.nlevels; ++l)
+            for (int q = sym.levelptr[l]; q < sym.levelptr[l + 1]; ++q) lvl[sym.level_fronts[q]] = l;
+        for (int l = 0; l < sym.nlevels; ++l) {
+            const int width = sym.levelptr[l + 1] - sym.levelptr[l];
+            for (int q = sym.levelptr[l]; q < sym.levelptr[l + 1]; ++q) {
+                const int f = sym.level_fronts[q];
+                int best = -1;
+                long long bsz = -1;
+                for (int ci = sym.f_childptr[f]; ci < sym.f_childptr[f + 1]; ++ci) {
+                    const int c = sym.f_children[ci];
+                    const long long uc = sym.f_nf[c] - sym.f_k[c];
+                    if (uc * (uc + 1) > bsz) { bsz = uc * (uc + 1); best = c; }
+                }
+                if (best >= 0 && width <= seq_env && lvl[best] == l - 1 && seqs[seq_of[best]].back() == best) {
+                    seq_of[f] = seq_of[best];
+                    seqs[seq_of[f]].push_back(f);
+                } else {
+                    seq_of[f] = (int)seqs.size();
+                    seqs.push_back(std::vector<int>(1, f));
+                }
+            }
+        }
+        std::vector<int> order(seqs.size()), slot(seqs.size(), 0);
+        for (size_t q = 0; q < seqs.size(); ++q) order[q] = (int)q;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return lvl[seqs[a].back()] < lvl[seqs[b].back()]; });
+        int nslots = 0;
+        for (int sq : order) {
+            for (int f : seqs[sq])
+                for (int ci = sym.f_childptr[f]; ci < sym.f_childptr[f + 1]; ++ci) {
+                    const int cs = seq_of[sym.f_children[ci]];
+                    if (cs != sq) slot[sq] = std::max(slot[sq], slot[cs] + 1);
+                }
+            nslots = std::max(nslots, slot[sq] + 1);
+        }
+        slot_seqptr.assign(1, 0);
+        for (int sl = 0; sl < nslots; ++sl) {
+            for (int sq : order)
+                if (slot[sq] == sl) {
+                    plan_seqptr.push_back((int)plan_fronts.size());
+                    for (int f : seqs[sq]) plan_fronts.push_back(f);
+                }
+            plan_levelptr.push_back((int)plan_fronts.size());
+            slot_seqptr.push_back((int)plan_seqptr.size());
+        }
+        plan_seqptr.push_back((int)plan_fronts.size());
+        for (int sl = 0; sl < nslots; ++sl) {
+            FactorLaunch fl{};
+            fl.begin = plan_levelptr[sl];
+            fl.count = plan_levelptr[sl + 1] - plan_levelptr[sl];
+            int mx = 0;
+            for (int q = fl.begin; q < fl.begin + fl.count; ++q) mx = std::max(mx, sym.f_nf[plan_fronts[q]]);
+            fl.dense_lu = true;
+            fl.ts = 1;
+            // a slot of a few chains is latency bound on its one or two CTAs: 512 threads; the wide slots at the bottom 256
+            fl.threads = fl.count <= 8 ? 512 : std::min(512, std::max(64, dense_lu_threads));
+            fl.smem = dense_lu_smem_doubles(mx) * sizeof(double);
+            fl.tr = 1;
+            fl.seq_begin = slot_seqptr[sl];
+            fl.nseq = slot_seqptr[sl + 1] - slot_seqptr[sl];
+            stage_dense_lu(fl);
+            fplan.push_back(fl);
+        }
+    } else {
+        for (int l = 0; l < sym.nlevels; ++l) {
+            for (int q = sym.levelptr[l]; q < sym.levelptr[l + 1]; ++q)
+                if (!in_task[sym.level_fronts[q]]) plan_fronts.push_back(sym.level_fronts[q]);
+            plan_levelptr.push_back((int)plan_fronts.size());
+        }
     }
-    for (int l = 0; l < sym.nlevels; ++l) {
+    for (int l = 0; l < sym.nlevels && !seq_mode; ++l) {
         int b = plan_levelptr[l], e = plan_levelptr[l + 1];
         int i = b;
         while (i < e) {   // fronts are sorted by decreasing order inside a level
@@ -1234,13 +1400,28 @@ void MfSolver::plan(int S) {
             fl.begin = i;
             fl.count = j - i;
             fl.dense = dense_ok(nf);
-            if (fl.dense) c = cls0(nf);
+            fl.dense_lu = dense_lu_ok(nf);
+            if (fl.dense || fl.dense_lu) c = cls0(nf);
+            if (fl.dense_lu) {
+                fl.ts = 1;
+                fl.threads = std::min(512, std::max(64, dense_lu_threads));
+                fl.smem = dense_lu_smem_doubles(nf) * sizeof(double);
+                fl.tr = 1;
+                fl.gstride = 0;
+                stage_dense_lu(fl);
+                fplan.push_back(fl);
+                i = j;
+                continue;
+            }
             fl.sym = symmetric && nf <= kMaxSymFront;
             fl.global_front = !fl.sym && (nf > kMaxSmemFront || c >= (int)rules.size());
             fl.bulk = false;
             if (fl.dense) {
                 fl.ts = 1;
                 fl.threads = nf <= dense_small ? 128 : 256;      // one thread per panel row is all step 2 can use
+                // a single case: the front is alone on its SM, gather / write-out / tensor tiles scale with the CTA width
+                // (measured 1.77 -> 1.38 ms per gain factorisation, 358 -> 428 GN iterations/s; JGB_DENSE_THREADS overrides)
+                if (S == 1) fl.threads = dense_threads_single > 0 ? std::min(512, dense_threads_single) : 512;
                 fl.smem = dense_smem_doubles(nf) * sizeof(double);
                 fl.tr = 1;
                 fl.gstride = 0;
@@ -1301,6 +1482,19 @@ void MfSolver::plan(int S) {
             } else if (!fl.bulk)
                 fl.smem = fl.global_front ? (size_t)(nf * 8 + 8 * (nf + 1)) * fl.ts * sizeof(double) : per * fl.ts;
             fl.gstride = (long long)nf * (nf + 1) * fl.ts;
+            if (staged_enabled && !fl.sym && !fl.bulk && !fl.global_front && fl.ts >= 2 && S % fl.ts == 0) {
+                // ring of two stages behind the largest front of the launch: the largest stage (8 KB .. 1 KB) that keeps
+                // the number of resident CTAs the front alone allows (at most 3: registers)
+                auto ctas = [](size_t bytes) { return std::min<size_t>(3, 233472 / (bytes + 1024)); };
+                size_t stage = 8192;
+                while (stage > 1024 && (ctas(fl.smem + 2 * stage) < ctas(fl.smem) || fl.smem + 2 * stage > 200 * 1024)) stage /= 2;
+                if (fl.smem + 2 * stage <= 200 * 1024 && ctas(fl.smem + 2 * stage) == ctas(fl.smem)) {
+                    fl.staged = true;
+                    fl.ring_elems = (int)(stage / (8 * fl.ts));
+                    fl.ring_off = (int)(fl.smem / 8);
+                    fl.smem += 2 * stage;
+                }
+            }
             if (fl.global_front)
                 gwork_need = std::max<size_t>(gwork_need, (size_t)fl.gstride * fl.count * (S / fl.ts));
             if (fl.smem > 200 * 1024) throw std::runtime_error("front too large for shared memory");
@@ -1315,7 +1509,32 @@ void MfSolver::plan(int S) {
                                                    {1 << 30, 1, 128}};
     const std::vector<PlanRule> brules = parse_rules("JGB_BPLAN_BATCH", bs_rules);
     auto bcls = [&](int nf) { size_t c = 0; while (c + 1 < brules.size() && nf > brules[c].maxnf) ++c; return (int)c; };
-    for (int d = 0; d < sym.ndepths; ++d) {
+    for (int sl_ = (int)slot_seqptr.size() - 2; seq_mode && sl_ >= 0; --sl_) {      // sequence mode: the factor slots backwards
+        SolveLaunch sl{};
+        sl.begin = plan_levelptr[sl_];
+        sl.count = plan_levelptr[sl_ + 1] - plan_levelptr[sl_];
+        sl.blocked = true;
+        sl.ts = 1;
+        sl.bs_rows = kBsRows;
+        sl.seq_begin = slot_seqptr[sl_];
+        sl.nseq = slot_seqptr[sl_ + 1] - slot_seqptr[sl_];
+        auto need = [&](int rows_) {
+            size_t worst = 0;
+            for (int q = sl.begin; q < sl.begin + sl.count; ++q) {
+                const int f = plan_fronts[q];
+                const int nf = sym.f_nf[f], kb = std::min(sym.f_k[f], rows_);
+                worst = std::max(worst, ((size_t)kb * (nf + 1) - (size_t)kb * (kb - 1) / 2 + nf) * sizeof(double));
+                sl.max_nf = std::max(sl.max_nf, nf);
+                sl.max_k = std::max(sl.max_k, sym.f_k[f]);
+            }
+            return worst;
+        };
+        while (sl.bs_rows > 1 && need(sl.bs_rows) > 200 * 1024) sl.bs_rows /= 2;
+        sl.smem = need(sl.bs_rows);
+        if (sl.smem > 200 * 1024) throw std::runtime_error("front too large for the back-solve staging buffer");
+        splan.push_back(sl);
+    }
+    for (int d = 0; d < sym.ndepths && !seq_mode; ++d) {
         int b = sym.depthptr[d], e = sym.depthptr[d + 1];
         int i = b;
         while (i < e) {
@@ -1395,7 +1614,8 @@ void MfSolver::plan(int S) {
         for (const SolveLaunch& sl : splan) {
             const bool reg = !sl.blocked && sl.max_nf <= backsolve_reg_max() && S % 32 == 0;
             const int w = sl.blocked ? 1 : reg ? 32 : sl.ts;
-            for (int q = sl.begin; q < sl.begin + sl.count; ++q) wu[sym.depth_fronts[q]] = std::min(w, wmax);
+            for (int q = sl.begin; q < sl.begin + sl.count; ++q)
+                wu[sl.nseq ? plan_fronts[q] : sym.depth_fronts[q]] = std::min(w, wmax);
         }
         std::vector<long long> uoff(F, 0), usecsz(6, 0);
         for (int f = 0; f < F; ++f) {
@@ -1480,6 +1700,59 @@ void MfSolver::plan(int S) {
             if (!cds.empty()) JGB_CUDA(cudaMemcpy(d_plan_child.p, cds.data(), cds.size() * sizeof(ChildDesc), cudaMemcpyHostToDevice));
             dev.child_desc = d_plan_child.p;
         }
+        // staged extend-add: destination of every update-storage element in its parent's front, and the chunk lists
+        std::vector<long long> cum(7, 0);
+        for (int q = 0; q < 6; ++q) cum[q + 1] = cum[q] + secsz[q];
+        std::vector<int> chunk_lo(F, 0), chunk_hi(F, 0);
+        {
+            bool any = false;
+            for (const FactorLaunch& fl : fplan) any = any || fl.staged;
+            if (any) {
+                std::vector<char> dense_lu_front(F, 0);
+                for (const FactorLaunch& fl : fplan)
+                    if (fl.dense_lu)
+                        for (int q = fl.begin; q < fl.begin + fl.count; ++q) dense_lu_front[plan_fronts[q]] = 1;
+                std::vector<int> dst((size_t)sym.upd_size, 0);
+                for (int c = 0; c < F; ++c) {
+                    const int par = sym.f_parent[c];
+                    if (par < 0) continue;
+                    const int uc = sym.f_nf[c] - sym.f_k[c];
+                    const int nfp = dense_lu_front[par] ? dense_lu_ld(sym.f_nf[par]) : sym.f_nf[par];     // column stride
+                    const int* rel = sym.f_rel.data() + sym.f_relptr[c];
+                    int* d = dst.data() + cum[lg2(wout[c])] + off[c];
+                    for (int j = 0; j <= uc; ++j) {
+                        const int dc = j < uc ? rel[j] : sym.f_nf[par];
+                        for (int i = 0; i < uc; ++i) d[(size_t)j * uc + i] = rel[i] + dc * nfp;
+                    }
+                }
+                std::vector<int> chunks;
+                for (FactorLaunch& fl : fplan) {
+                    if (!fl.staged) continue;
+                    fl.sec_cum = (int)cum[lg2(fl.ts)];
+                    for (int q = fl.begin; q < fl.begin + fl.count; ++q) {
+                        const int f = plan_fronts[q];
+                        chunk_lo[f] = (int)(chunks.size() / 2);
+                        for (int ci = sym.f_childptr[f]; ci < sym.f_childptr[f + 1]; ++ci) {
+                            const int c = sym.f_children[ci];
+                            const long long uc = sym.f_nf[c] - sym.f_k[c], total = uc * (uc + 1);
+                            for (long long e = 0; e < total; e += fl.ring_elems) {
+                                chunks.push_back((int)(off[c] + e));
+                                chunks.push_back((int)std::min<long long>(fl.ring_elems, total - e));
+                            }
+                        }
+                        chunk_hi[f] = (int)(chunks.size() / 2);
+                    }
+                }
+                d_upd_dst.alloc(dst.size());
+                d_chunks.alloc(std::max<size_t>(chunks.size(), 2));
+                if (!dst.empty()) JGB_CUDA(cudaMemcpy(d_upd_dst.p, dst.data(), dst.size() * sizeof(int), cudaMemcpyHostToDevice));
+                if (!chunks.empty()) JGB_CUDA(cudaMemcpy(d_chunks.p, chunks.data(), chunks.size() * sizeof(int), cudaMemcpyHostToDevice));
+            }
+        }
+        std::vector<char> is_staged(F, 0);
+        for (const FactorLaunch& fl : fplan)
+            if (fl.staged)
+                for (int q = fl.begin; q < fl.begin + fl.count; ++q) is_staged[plan_fronts[q]] = 1;
         // per-front descriptors in launch order. Fronts factored on packed lower triangles (LDL^T kernels) take the
         // symmetric gather lists, and a front whose parent is such a front writes only the lower triangle of its block.
         std::vector<FrontDesc> descs(plan_fronts.size());
@@ -1489,12 +1762,17 @@ void MfSolver::plan(int S) {
             d.f = f; d.nf = sym.f_nf[f]; d.k = sym.f_k[f]; d.rowptr = sym.f_rowptr[f];
             d.asm0 = sym.f_asmptr[f]; d.asm1 = sym.f_asmptr[f + 1];
             d.child0 = sym.f_childptr[f]; d.child1 = sym.f_childptr[f + 1];
+            if (is_staged[f]) { d.child0 = chunk_lo[f]; d.child1 = chunk_hi[f]; }      // chunk range instead
             if (lower[f]) { d.ea0 = sym.f_eaptr_sym[f]; d.ea1 = sym.f_eaptr_sym[f + 1]; }
             else { d.ea0 = sym.f_eaptr[f]; d.ea1 = sym.f_eaptr[f + 1]; }
             const int par = sym.f_parent[f];
             d.flags = ((par >= 0 && lower[par]) ? 1 : 0) | (wu[f] << 8);
             d.wout = wout[f];
             d.uoff = uoff[f]; d.updoff = off[f];
+        }
+        if (seq_mode) {
+            d_seqptr.alloc(plan_seqptr.size());
+            JGB_CUDA(cudaMemcpy(d_seqptr.p, plan_seqptr.data(), plan_seqptr.size() * sizeof(int), cudaMemcpyHostToDevice));
         }
         d_plan_desc.alloc(descs.size());
         d_plan_fronts.alloc(plan_fronts.size());
@@ -1504,10 +1782,68 @@ void MfSolver::plan(int S) {
                                 cudaMemcpyHostToDevice));
         }
     }
+    {
+        // DAG schedule (batches): one in-order stream per launch class; a launch waits for the latest launch of every
+        // other stream that holds a child of one of its fronts. JGB_LANES=1 keeps everything on the caller's stream.
+        static const int lanes_env = getenv("JGB_LANES") ? atoi(getenv("JGB_LANES")) : 0;
+        nlanes = 1;
+        if (S > 1 && tplan.empty() && lanes_env != 1) {
+            std::vector<long long> keys;       // class key -> lane
+            std::vector<int> launch_of(sym.nfronts, -1);
+            for (size_t i = 0; i < fplan.size(); ++i) {
+                FactorLaunch& fl = fplan[i];
+                const long long key = fl.global_front ? 1 : fl.dense ? 2 : fl.dense_lu ? 3 : fl.bulk ? 100 + fl.maxnf : fl.sym ? 200 + fl.ts : 300 + fl.ts;
+                size_t l = 0;
+                while (l < keys.size() && keys[l] != key) ++l;
+                if (l == keys.size()) keys.push_back(key);
+                fl.lane = (int)l;
+                if (lanes_env > 1) fl.lane %= lanes_env;
+                for (int q = fl.begin; q < fl.begin + fl.count; ++q) launch_of[plan_fronts[q]] = (int)i;
+            }
+            nlanes = lanes_env > 1 ? std::min<int>(lanes_env, (int)keys.size()) : (int)keys.size();
+            for (size_t i = 0; i < fplan.size(); ++i) {
+                FactorLaunch& fl = fplan[i];
+                std::vector<int> latest(nlanes, -1);
+                for (int q = fl.begin; q < fl.begin + fl.count; ++q) {
+                    const int f = plan_fronts[q];
+                    for (int ci = sym.f_childptr[f]; ci < sym.f_childptr[f + 1]; ++ci) {
+                        const int li = launch_of[sym.f_children[ci]];
+                        if (li >= 0 && fplan[li].lane != fl.lane) latest[fplan[li].lane] = std::max(latest[fplan[li].lane], li);
+                    }
+                }
+                fl.deps.clear();
+                for (int l = 0; l < nlanes; ++l)
+                    if (latest[l] >= 0) { fl.deps.push_back(latest[l]); fplan[latest[l]].record = true; }
+            }
+            while ((int)lanes.size() < nlanes - 1) {
+                cudaStream_t x;
+                JGB_CUDA(cudaStreamCreateWithFlags(&x, cudaStreamNonBlocking));
+                lanes.push_back(x);
+            }
+            while (lane_events.size() < fplan.size() + (size_t)nlanes) {
+                cudaEvent_t e;
+                JGB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                lane_events.push_back(e);
+            }
+            if (!fork_event) JGB_CUDA(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
+        }
+    }
+    if (getenv("JGB_PLAN_DEBUG")) {
+        for (const FactorLaunch& fl : fplan)
+            fprintf(stderr, "[plan S=%d] fronts %4d nf<=%3d ts %2d threads %4d smem %6zu %s%s%s%s%s ring %d\n", S, fl.count,
+                    sym.f_nf[plan_fronts[fl.begin]], fl.ts, fl.threads, fl.smem, fl.bulk ? "bulk " : "", fl.sym ? "sym " : "",
+                    fl.dense ? "dense " : fl.dense_lu ? "denselu " : "", fl.global_front ? "global " : "", fl.staged ? "staged" : "", fl.ring_elems);
+    }
     d_U.alloc((size_t)sym.u_size * S);
     d_upd.alloc((size_t)sym.upd_size * S);
     if (gwork_need) d_gwork.alloc(gwork_need);
     planned_S = S;
+}
+
+MfSolver::~MfSolver() {
+    for (cudaStream_t x : lanes) cudaStreamDestroy(x);
+    for (cudaEvent_t e : lane_events) cudaEventDestroy(e);
+    if (fork_event) cudaEventDestroy(fork_event);
 }
 
 int MfSolver::launches_per_solve(int S) {
@@ -1527,9 +1863,35 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
     for (const TaskLaunch& tl : tplan)
         launch_task(tl.te, tl.maxnf, dim3(tl.count, S / 32), tl.smem, st, dev, d_task_blob.p, d_task_desc.p + tl.begin,
                     aval, rhs, d_U.p, d_upd.p, S, tl.front_cap, tl.stack_cap, active, status);
-    for (const FactorLaunch& fl : fplan) {
+    if (nlanes > 1) {
+        JGB_CUDA(cudaEventRecord(fork_event, st));
+        for (int l = 1; l < nlanes; ++l) JGB_CUDA(cudaStreamWaitEvent(lanes[l - 1], fork_event, 0));
+    }
+    cudaStream_t const st0 = st;
+    auto staged_args = [&](const FactorLaunch& fl) {
+        StagedEa sg{};
+        if (fl.staged) {
+            sg.chunks = reinterpret_cast<const int2*>(d_chunks.p);
+            sg.upd_dst = d_upd_dst.p;
+            sg.sec_cum = fl.sec_cum; sg.ring_elems = fl.ring_elems; sg.ring_off = fl.ring_off;
+        }
+        return sg;
+    };
+    for (size_t li = 0; li < fplan.size(); ++li) {
+        const FactorLaunch& fl = fplan[li];
         dim3 grid(fl.count, S / fl.ts);
-        if (fl.dense)
+        if (nlanes > 1) {
+            st = fl.lane == 0 ? st0 : lanes[fl.lane - 1];
+            for (int d : fl.deps) JGB_CUDA(cudaStreamWaitEvent(st, lane_events[d], 0));
+        }
+        if (fl.dense_lu && fl.nseq)
+            mf_factor_dense_lu_kernel<<<dim3(fl.nseq, S), fl.threads, fl.smem, st>>>(dev, d_plan_desc.p, aval, rhs, d_U.p, d_upd.p,
+                                                                                     S, active, status, d_seqptr.p + fl.seq_begin,
+                                                                                     staged_args(fl));
+        else if (fl.dense_lu)
+            mf_factor_dense_lu_kernel<<<grid, fl.threads, fl.smem, st>>>(dev, d_plan_desc.p + fl.begin, aval, rhs, d_U.p,
+                                                                          d_upd.p, S, active, status, nullptr, staged_args(fl));
+        else if (fl.dense)
             mf_factor_dense_sym_kernel<<<grid, fl.threads, fl.smem, st>>>(dev, d_plan_desc.p + fl.begin, aval, rhs, d_U.p,
                                                                            d_upd.p, S, active, status);
         else if (fl.bulk)
@@ -1542,16 +1904,30 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
         else if (fl.sym)
             launch_factor_sym(fl.ts, grid, fl.threads, fl.smem, st, dev, d_plan_desc.p + fl.begin, aval, rhs, d_U.p,
                               d_upd.p, S, fl.tr, active, status);
-        else
+        else {
+            const StagedEa sg = staged_args(fl);
             launch_factor<false>(fl.ts, grid, fl.threads, fl.smem, st, dev, d_plan_fronts.p + fl.begin,
                                  d_plan_desc.p + fl.begin, aval, rhs, d_U.p, d_upd.p, S, fl.tr,
-                                 active, status, nullptr, 0);
+                                 active, status, nullptr, 0, sg);
+        }
+        if (nlanes > 1 && fl.record) JGB_CUDA(cudaEventRecord(lane_events[li], st));
+    }
+    if (nlanes > 1) {          // join: the caller's stream waits for the tail of every lane
+        st = st0;
+        for (int l = 1; l < nlanes; ++l) {
+            cudaEvent_t e = lane_events[fplan.size() + l];
+            JGB_CUDA(cudaEventRecord(e, lanes[l - 1]));
+            JGB_CUDA(cudaStreamWaitEvent(st, e, 0));
+        }
     }
     if (after_factor) JGB_CUDA(cudaEventRecord(after_factor, st));
     for (const SolveLaunch& sl : splan) {
-        if (sl.blocked) {
+        if (sl.blocked && sl.nseq) {
+            mf_backsolve_single<<<dim3(sl.nseq, S), backsolve_single_threads(), sl.smem, st>>>(dev, d_plan_fronts.p, d_U.p, x, active, S,
+                                                                                              sl.bs_rows, d_seqptr.p + sl.seq_begin);
+        } else if (sl.blocked) {
             mf_backsolve_single<<<dim3(sl.count, S), backsolve_single_threads(), sl.smem, st>>>(dev, d_depth_fronts.p + sl.begin, d_U.p, x,
-                                                                        active, S, sl.bs_rows);
+                                                                        active, S, sl.bs_rows, nullptr);
         } else if (sl.max_nf <= backsolve_reg_max() && S % 32 == 0) {
             launch_backsolve_reg(sl.max_nf, sl.count, S, st, dev, d_depth_fronts.p + sl.begin, d_U.p, x, active);
         } else {

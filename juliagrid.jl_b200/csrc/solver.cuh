@@ -5,6 +5,7 @@
 // One instance owns the device copy of a `Symbolic` and the factor workspaces for up to S scenarios;
 // values are laid out scenario-minor: element e of scenario s lives at [e * S + s].
 #pragma once
+#include <vector>
 #include "common.cuh"
 #include "symbolic.hpp"
 #include "tasks.hpp"
@@ -53,6 +54,16 @@ struct __align__(16) ChildDesc {
     long long updoff;
 };
 
+// Staged extend-add of the scenario-tile LU kernel (see mf_factor_kernel): chunk list (x = element offset inside the
+// tile's section, y = elements), destination list in update-storage order, ring geometry
+struct StagedEa {
+    const int2* chunks = nullptr;
+    const int* upd_dst = nullptr;
+    int sec_cum = 0;        // elements of the sections below this launch's tile width (index base into upd_dst)
+    int ring_elems = 0;     // elements per ring stage
+    int ring_off = 0;       // doubles from the start of dynamic shared memory to the ring
+};
+
 struct FactorLaunch {
     int begin, count;      // range in level_fronts
     int ts;                // scenarios per CTA
@@ -63,9 +74,20 @@ struct FactorLaunch {
     bool bulk;             // TMA-staged small-front kernel (batch only)
     bool sym;              // packed symmetric (LDL^T) kernel
     bool dense;            // one-scenario-per-CTA LDL^T kernel with the tensor-core trailing update (mf_dense.cuh)
+    bool dense_lu;         // its LU twin for unsymmetric values (mf_factor_dense_lu_kernel)
+    // single case: a CTA walks a chain of fronts (each the parent of the one before) without leaving the kernel;
+    // launches follow dependency slots instead of tree levels (see MfSolver::plan)
+    int seq_begin = 0, nseq = 0;   // range in the sequence-pointer array; 0 sequences = one CTA per front
     int maxnf;             // bulk: register bound on the front order (kernel variant)
     int smem_elems;        // bulk: front + staging capacity in elements (x 32 lanes x 8 bytes)
     long long gstride;
+    bool staged;           // extend-add through the cp.async.bulk ring (LU scenario-tile kernel, batches)
+    int ring_elems, ring_off, sec_cum;
+    // batches: launches form a DAG (a launch waits only for the launches that hold children of its fronts); every
+    // launch class has its own in-order stream, cross-stream edges are events
+    int lane = 0;                  // stream index (0 = the caller's stream)
+    bool record = false;           // some launch on another stream waits for this one
+    std::vector<int> deps;         // launches on other streams to wait for (the latest per stream)
 };
 
 struct SolveLaunch {
@@ -75,6 +97,7 @@ struct SolveLaunch {
     size_t smem;
     int bs_rows;           // rows per block of the blocked kernel (<= 32)
     bool blocked;          // 32-row blocked kernel (single case; batch fronts too large for the tile staging)
+    int seq_begin = 0, nseq = 0;   // sequences of this launch (walked from the last front to the first)
 };
 
 class MfSolver {
@@ -116,7 +139,9 @@ class MfSolver {
     TaskPlan task_plan;
     std::vector<char> in_task;             // front is factored by a task launch (not by fplan)
     std::vector<int> plan_levelptr, plan_fronts;   // level schedule of the fronts left to fplan
-    DevBuf<int> d_task_blob, d_plan_fronts, d_plan_pair, d_plan_pair_s;
+    DevBuf<int> d_task_blob, d_plan_fronts, d_plan_pair, d_plan_pair_s, d_upd_dst, d_chunks, d_seqptr;
+    std::vector<int> plan_seqptr;          // sequence starts in plan_fronts (+ end), sequence mode only
+    bool seq_mode = false;
     DevBuf<ChildDesc> d_plan_child;
     DevBuf<long long> d_plan_uoff;
     DevBuf<int2> d_task_desc;
@@ -137,6 +162,13 @@ class MfSolver {
     DevBuf<FrontDesc> d_level_desc;
     DevBuf<ChildDesc> d_child_desc;
     DevSym dev{};
+    // DAG schedule of the batch factor phase
+    std::vector<cudaStream_t> lanes;       // auxiliary streams (lane l > 0 -> lanes[l - 1])
+    std::vector<cudaEvent_t> lane_events;  // one per factor launch
+    cudaEvent_t fork_event = nullptr;
+    int nlanes = 1;
+  public:
+    ~MfSolver();
 };
 
 }  // namespace jgb
