@@ -562,9 +562,10 @@ template <int TE, int MAXNF>
 __global__ void __launch_bounds__(32 * TE)
 mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const double* __restrict__ aval,
                       const double* __restrict__ rhs, double* __restrict__ U, double* __restrict__ upd, int S,
-                      int smem_elems, const unsigned char* __restrict__ active, int* __restrict__ status) {
+                      int smem_elems, const unsigned char* __restrict__ active, int* __restrict__ status, StagedEa sg) {
     extern __shared__ __align__(128) double sm[];
     __shared__ __align__(8) uint64_t mbar;
+    __shared__ __align__(8) uint64_t ea_bar[2];
     __shared__ int s_off[kBulkMaxChildren], s_uc[kBulkMaxChildren], s_relo[kBulkMaxChildren], s_relp[kBulkMaxChildren], s_gend;
     __shared__ long long s_updoff[kBulkMaxChildren];
     constexpr int TR = TE >= 4 ? 4 : TE, TC = TE / TR;
@@ -584,7 +585,24 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
     double* __restrict__ uptile = upd + sy.sec_base[5] + (long long)blockIdx.y * sy.sec_size[5] * 32;   // section W = 32
     const int c0 = fd.child0, c1 = fd.child1;
 
-    if (threadIdx.x == 0 && c1 > c0) mbar_init(&mbar, 1);
+    // Ring mode (sg.chunks): the children's blocks stream through a two-stage ring behind the front in chunks of one child
+    // (child order), destinations from the list in update-storage order. The staging area no longer has to hold the
+    // largest child: 13-16-row fronts go from one CTA per SM (front + 45-60 KB of staging) to two or three.
+    const bool ring_mode = sg.chunks != nullptr;
+    const int nch = ring_mode ? c1 - c0 : 0;      // child0 / child1 hold the chunk range in ring mode
+    if (threadIdx.x == 0 && c1 > c0) {
+        if (ring_mode) {
+            mbar_init(&ea_bar[0], 1);
+            mbar_init(&ea_bar[1], 1);
+            for (int c = 0; c < 2 && c < nch; ++c) {
+                const int2 cd = sg.chunks[c0 + c];
+                mbar_expect_tx(&ea_bar[c], (uint32_t)cd.y * 256u);
+                bulk_g2s(stage + (size_t)c * sg.ring_elems * 32, uptile + (size_t)cd.x * 32, (uint32_t)cd.y * 256u, &ea_bar[c]);
+            }
+        } else {
+            mbar_init(&mbar, 1);
+        }
+    }
     // matrix entries and right-hand side: the first few per lane are fetched into registers before the front is
     // zeroed, so their index -> value load chains overlap the zeroing pass and the barrier instead of following them
     constexpr int NPRE = 6;
@@ -623,8 +641,32 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
         }
         for (int p = e0 + NPRE_R * TE; p < k; p += TE) Fl[(p + nf * nf) * 32] = rhs[wide(rows[p], S) + s];
     }
+    if (ring_mode) {
+        __syncthreads();                          // front assembled, barriers initialised
+        for (int c = 0; c < nch; ++c) {
+            const int2 cd = sg.chunks[c0 + c];
+            const int* __restrict__ dl = sg.upd_dst + sg.sec_cum + cd.x;
+            constexpr int NQ = 4;
+            int dq[NQ];
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) dq[q] = (e0 + q * TE < cd.y) ? dl[e0 + q * TE] : -1;
+            mbar_wait(&ea_bar[c & 1], (c >> 1) & 1);
+            const double* rg = stage + (size_t)(c & 1) * sg.ring_elems * 32 + sl;
+#pragma unroll
+            for (int q = 0; q < NQ; ++q)
+                if (dq[q] >= 0) Fl[dq[q] * 32] += rg[(e0 + q * TE) * 32];
+            for (int e = e0 + NQ * TE; e < cd.y; e += TE) Fl[dl[e] * 32] += rg[e * 32];
+            __syncthreads();
+            if (threadIdx.x == 0 && c + 2 < nch) {
+                const int2 nd = sg.chunks[c0 + c + 2];
+                mbar_expect_tx(&ea_bar[c & 1], (uint32_t)nd.y * 256u);
+                bulk_g2s(stage + (size_t)(c & 1) * sg.ring_elems * 32, uptile + (size_t)nd.x * 32, (uint32_t)nd.y * 256u,
+                         &ea_bar[c & 1]);
+            }
+        }
+    }
     uint32_t parity = 0;
-    for (int ci = c0; ci < c1;) {
+    for (int ci = c0; ci < c1 && !ring_mode;) {
         // child descriptors of up to kBulkMaxChildren children: one parallel 16-byte read each (no dependent chain)
         const int ncand = min(c1 - ci, kBulkMaxChildren);
         if ((int)threadIdx.x < ncand) {
@@ -767,11 +809,11 @@ void launch_factor(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st,
 
 void launch_factor_bulk(int maxnf, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const FrontDesc* fronts,
                         const double* aval, const double* rhs, double* U, double* upd, int S, int smem_elems,
-                        const unsigned char* active, int* status) {
+                        const unsigned char* active, int* status, StagedEa sg) {
 #define X(TE, MAXNF)                                                                                              \
     if (maxnf == MAXNF) {                                                                                         \
         mf_factor_bulk_kernel<TE, MAXNF><<<grid, 32 * TE, smem, st>>>(dev, fronts, aval, rhs, U, upd, S, smem_elems, \
-                                                                      active, status);                           \
+                                                                      active, status, sg);                       \
         return;                                                                                                   \
     }
     JGB_BULK_VARIANTS(X)
@@ -1259,6 +1301,7 @@ void MfSolver::plan(int S) {
     const bool bulk_enabled = !(nb && *nb == '1');
     // JGB_STAGED_EA=0 falls back to the gather in rounds (A/B runs)
     static const bool staged_enabled = !(getenv("JGB_STAGED_EA") && atoi(getenv("JGB_STAGED_EA")) == 0);
+    static const bool bulk_ring = !(getenv("JGB_BULK_RING") && atoi(getenv("JGB_BULK_RING")) == 0);
     const std::vector<PlanRule> rules = (S == 1) ? parse_rules("JGB_FPLAN_SINGLE", symmetric ? single_rules_sym : single_rules)
                                                  : parse_rules("JGB_FPLAN_BATCH", symmetric ? batch_rules_sym : batch_rules);
     // LDL^T fronts above dense_min rows take the one-scenario-per-CTA kernel with the FP64 tensor-core trailing update.
@@ -1446,7 +1489,27 @@ void MfSolver::plan(int S) {
                     need = std::max(need, fsz + std::max(2 * fl.maxnf, std::min(total_c, std::max(largest, 192))));
                 }
                 size_t bytes = (size_t)need * 256 + (size_t)need * 4 + 64;
-                if (bytes <= 200 * 1024) {
+                if (bulk_ring) {
+                    // ring mode: front + two stages of 64 / 32 / 16 elements (16 / 8 / 4 KB), whichever keeps the most
+                    // CTAs resident (ties: the larger stage); the ring also holds the two pivot strips (2 x maxnf elements)
+                    int fmax = 0;
+                    for (int q = i; q < j; ++q) fmax = std::max(fmax, sym.f_nf[plan_fronts[q]] * (sym.f_nf[plan_fronts[q]] + 1));
+                    int best_stage = 0;
+                    size_t best_ctas = 0;
+                    for (int stg : {64, 32, 16}) {
+                        if (2 * stg < 2 * fl.maxnf) continue;
+                        const size_t b = (size_t)(fmax + 2 * stg) * 256;
+                        const size_t ctas = std::min<size_t>(2048 / (32 * bulk_lanes_for(fl.maxnf)), 233472 / (b + 1024));
+                        if (ctas > best_ctas) { best_ctas = ctas; best_stage = stg; }
+                    }
+                    fl.bulk = true;
+                    fl.ts = 32;
+                    fl.staged = true;
+                    fl.ring_elems = best_stage;
+                    fl.smem_elems = fmax + 2 * best_stage;
+                    fl.threads = 32 * bulk_lanes_for(fl.maxnf);
+                    fl.smem = (size_t)fl.smem_elems * 256 + 64;
+                } else if (bytes <= 200 * 1024) {
                     fl.bulk = true;
                     fl.ts = 32;
                     fl.smem_elems = need;
@@ -1896,7 +1959,7 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
                                                                            d_upd.p, S, active, status);
         else if (fl.bulk)
             launch_factor_bulk(fl.maxnf, grid, fl.smem, st, dev, d_plan_desc.p + fl.begin, aval, rhs, d_U.p,
-                               d_upd.p, S, fl.smem_elems, active, status);
+                               d_upd.p, S, fl.smem_elems, active, status, staged_args(fl));
         else if (fl.global_front)
             launch_factor<true>(fl.ts, grid, fl.threads, fl.smem, st, dev, d_plan_fronts.p + fl.begin,
                                 d_plan_desc.p + fl.begin, aval, rhs, d_U.p, d_upd.p, S, fl.tr,
