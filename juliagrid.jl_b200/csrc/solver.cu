@@ -883,13 +883,13 @@ void launch_factor(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st,
 }
 
 // (lanes per scenario, register bound on the front order) variants of the bulk kernel
-#define JGB_BULK_VARIANTS(X) X(4, 8) X(4, 12) X(8, 16)
+#define JGB_BULK_VARIANTS(X) X(4, 8) X(8, 8) X(4, 12) X(8, 12) X(8, 16) X(16, 16)
 
-void launch_factor_bulk(int maxnf, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const FrontDesc* fronts,
+void launch_factor_bulk(int maxnf, int te, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const FrontDesc* fronts,
                         const double* aval, const double* rhs, double* U, double* upd, int S, int smem_elems,
                         const unsigned char* active, int* status, StagedEa sg) {
 #define X(TE, MAXNF)                                                                                              \
-    if (maxnf == MAXNF) {                                                                                         \
+    if (maxnf == MAXNF && te == TE) {                                                                             \
         mf_factor_bulk_kernel<TE, MAXNF><<<grid, 32 * TE, smem, st>>>(dev, fronts, aval, rhs, U, upd, S, smem_elems, \
                                                                       active, status, sg);                       \
         return;                                                                                                   \
@@ -906,7 +906,17 @@ int bulk_variant_for(int nf) {
     if (nf > bulk_max || nf > 16) return 0;
     return nf <= 8 ? 8 : nf <= 12 ? 12 : 16;
 }
-int bulk_lanes_for(int maxnf) { return maxnf <= 12 ? 4 : 8; }
+// warps per CTA of the small-front kernel by register variant; JGB_BULK_LANES="a,b,c" overrides (tuning only)
+int bulk_lanes_for(int maxnf) {
+    // measured at 10 016 scenarios (factor phase): 4,4,8 38.6 ms; 4,8,8 37.3; 8,8,8 39.8; 4,8,16 42.3
+    static int v[3] = {4, 8, 8};
+    static bool init = false;
+    if (!init) {
+        init = true;
+        if (const char* e = getenv("JGB_BULK_LANES")) sscanf(e, "%d,%d,%d", &v[0], &v[1], &v[2]);
+    }
+    return maxnf <= 8 ? v[0] : maxnf <= 12 ? v[1] : v[2];
+}
 
 template <int TS>
 void set_factor_smem_attr() {
@@ -2036,7 +2046,7 @@ void MfSolver::factor_solve(const double* aval, const double* rhs, double* x, in
             mf_factor_dense_sym_kernel<<<grid, fl.threads, fl.smem, st>>>(dev, d_plan_desc.p + fl.begin, aval, rhs, d_U.p,
                                                                            d_upd.p, S, active, status);
         else if (fl.bulk)
-            launch_factor_bulk(fl.maxnf, grid, fl.smem, st, dev, d_plan_desc.p + fl.begin, aval, rhs, d_U.p,
+            launch_factor_bulk(fl.maxnf, fl.threads / 32, grid, fl.smem, st, dev, d_plan_desc.p + fl.begin, aval, rhs, d_U.p,
                                d_upd.p, S, fl.smem_elems, active, status, staged_args(fl));
         else if (fl.global_front)
             launch_factor<true>(fl.ts, grid, fl.threads, fl.smem, st, dev, d_plan_fronts.p + fl.begin,

@@ -1,6 +1,7 @@
 #!/bin/bash
-wls() { echo "== $*"; env "$@" python scripts/time_wls.py 1000 2>&1 | grep -E "single WLS|batch WLS|rror"; }
-wls JGB_DENSE_THREADS=256
-wls JGB_DENSE_THREADS=512
-wls JGB_DENSE_THREADS=1024
-wls JGB_DENSE_THREADS=768
+nr() { echo "== $*"; env "$@" python scripts/time_nr.py 10016 2>&1 | grep -E "batch S|rror" | sed 's/; status.*//'; }
+nr JGB_BULK_LANES=4,4,8
+nr JGB_BULK_LANES=4,8,8
+nr JGB_BULK_LANES=8,8,8
+nr JGB_BULK_LANES=4,8,16
+nr JGB_BULK_LANES=4,4,16
