@@ -888,9 +888,9 @@ int WlsContext::batch(int64_t Sreal64, const double* Z, bool dev_in, int64_t max
     wls_broadcast_kernel<<<(int)((ns + 255) / 256), 256, 0, stream>>>(d_vm.p, b_vm.p, n, S);
     wls_broadcast_kernel<<<(int)((ns + 255) / 256), 256, 0, stream>>>(d_va.p, b_va.p, n, S);
     // constant H entries (codes 1, 12, 13) and zeros for out-of-service rows
-    DevBuf<double> hc;
-    hc.upload(h_const, stream);
-    wls_broadcast_kernel<<<(int)((hs + 255) / 256), 256, 0, stream>>>(hc.p, b_hval.p, nnzh, S);
+    b_hconst.upload(h_const, stream);      // persistent buffer: a cudaMalloc / cudaFree pair per batch costs 50-250 ms once
+                                           // tens of GB are allocated (seen as WLS 448 vs 241 ms per step beside the NR context)
+    wls_broadcast_kernel<<<(int)((hs + 255) / 256), 256, 0, stream>>>(b_hconst.p, b_hval.p, nnzh, S);
     JGB_CUDA(cudaMemsetAsync(b_res.p, 0, (size_t)m * S * sizeof(double), stream));
     launches += 5;
     WlsDev d = view(true);

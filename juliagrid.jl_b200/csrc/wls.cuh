@@ -117,7 +117,7 @@ class WlsContext {
     DevBuf<int> d_status, d_iters, d_remaining;
     // batch state
     int batch_S = 0;
-    DevBuf<double> b_vm, b_va, b_z, b_res, b_hval, b_gval, b_rhs, b_inc, b_objpart, b_obj, b_maxinc, b_out, b_zraw;
+    DevBuf<double> b_vm, b_va, b_z, b_res, b_hval, b_gval, b_rhs, b_inc, b_objpart, b_obj, b_maxinc, b_out, b_zraw, b_hconst;
     DevBuf<unsigned long long> b_maxbits;
     DevBuf<unsigned char> b_active;
     DevBuf<int> b_status, b_iters;

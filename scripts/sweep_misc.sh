@@ -1,7 +1,9 @@
 #!/bin/bash
-nr() { echo "== $*"; env "$@" python scripts/time_nr.py 10016 2>&1 | grep -E "batch S|rror" | sed 's/; status.*//'; }
-nr JGB_BULK_LANES=4,4,8
-nr JGB_BULK_LANES=4,8,8
-nr JGB_BULK_LANES=8,8,8
-nr JGB_BULK_LANES=4,8,16
-nr JGB_BULK_LANES=4,4,16
+b() { echo "== $*"; env "$@" python bench.py --workload wls --steps 3 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], {k:round(v['ms'],2) for k,v in d['roofline']['per_phase'].items()})
+"; }
+b JGB_LANES=1
+b JGB_LANES=0
+b JGB_LANES=1 JGB_BULK_RING=0
