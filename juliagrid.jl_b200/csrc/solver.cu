@@ -67,6 +67,64 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     } while (!ok);
 }
 
+// Trailing update A22 -= L21 U12 of one panel of PB pivots (see mf_factor_kernel): lane (er, ec) owns rows er, er + TR, ...
+// in pairs and every TC-th column; the PB multipliers of its two rows stay in registers, the pivot-row entries are
+// shared-memory broadcasts.
+template <int TS, int PB, bool GLOBAL_F>
+__device__ __forceinline__ void trailing_update(double* Fl, const double* pan, const double* Ul, int nf, int p0, int pe,
+                                                int er, int ec, int TR, int TC) {
+    constexpr int B = 8;
+    const int colstride = nf * TS;
+    for (int i = pe + er; i < nf; i += 2 * TR) {
+        const int i2 = i + TR;
+        const bool two = i2 < nf;
+        double* rowi = Fl + i * TS;
+        double* rowi2 = Fl + (two ? i2 : i) * TS;
+        double l[PB], l2[PB];
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+            l[q] = pan[(i + q * nf) * TS];
+            l2[q] = two ? pan[(i2 + q * nf) * TS] : 0.0;
+        }
+        int j = pe + ec;
+        for (; j + TC <= nf; j += 2 * TC) {
+            const double *ua, *ub;
+            if constexpr (GLOBAL_F) { ua = Ul + j * B * TS; ub = Ul + (j + TC) * B * TS; }
+            else { ua = Fl + (p0 + j * nf) * TS; ub = Fl + (p0 + (j + TC) * nf) * TS; }
+            double a1 = rowi[j * colstride], a2 = rowi2[j * colstride];
+            double b1 = rowi[(j + TC) * colstride], b2 = rowi2[(j + TC) * colstride];
+#pragma unroll
+            for (int q = 0; q < PB; ++q) {
+                const double x = ua[q * TS], y = ub[q * TS];
+                a1 -= l[q] * x;
+                a2 -= l2[q] * x;
+                b1 -= l[q] * y;
+                b2 -= l2[q] * y;
+            }
+            rowi[j * colstride] = a1;
+            rowi[(j + TC) * colstride] = b1;
+            if (two) {
+                rowi2[j * colstride] = a2;
+                rowi2[(j + TC) * colstride] = b2;
+            }
+        }
+        if (j <= nf) {
+            const double* ua;
+            if constexpr (GLOBAL_F) ua = Ul + j * B * TS;
+            else ua = Fl + (p0 + j * nf) * TS;
+            double a1 = rowi[j * colstride], a2 = rowi2[j * colstride];
+#pragma unroll
+            for (int q = 0; q < PB; ++q) {
+                const double x = ua[q * TS];
+                a1 -= l[q] * x;
+                a2 -= l2[q] * x;
+            }
+            rowi[j * colstride] = a1;
+            if (two) rowi2[j * colstride] = a2;
+        }
+    }
+}
+
 constexpr int kEaChunkCache = 96;      // chunk descriptors of a front kept in shared memory (ring-mode extend-add)
 
 // One CTA = one front x TS scenarios. Thread t: scenario lane sl = t % TS, entry lane e = t / TS,
@@ -74,7 +132,7 @@ constexpr int kEaChunkCache = 96;      // chunk descriptors of a front kept in s
 // element (r,c) of scenario lane sl at F[(r + c*nf) * TS + sl].  TS and the address space of F are compile-time
 // so that the front is addressed with LDS/STS and shifts (a runtime select would degrade to generic LD/ST).
 template <int TS, bool GLOBAL_F>
-__global__ void __launch_bounds__(TS == 1 ? 512 : 256)
+__global__ void __launch_bounds__(TS == 1 ? 512 : 256, TS == 1 ? 1 : 3)
 mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __restrict__ descs,
                  const double* __restrict__ aval, const double* __restrict__ rhs, double* __restrict__ U,
                  double* __restrict__ upd, int S, int TR, const unsigned char* __restrict__ active,
@@ -352,53 +410,18 @@ mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __r
             }
         }
         __syncthreads();
-        // two rows per lane (i and i + TR) share every pivot-row read: 8 broadcast LDS feed 16 multiply-adds
-        for (int i = pe + er; i < nf; i += 2 * TR) {
-            const int i2 = i + TR;
-            const bool two = i2 < nf;
-            double* rowi = Fl + i * TS;
-            double* rowi2 = Fl + (two ? i2 : i) * TS;
-            double l[B], l2[B];
-#pragma unroll
-            for (int q = 0; q < B; ++q) {
-                l[q] = (q < pb) ? pan[(i + q * nf) * TS] : 0.0;
-                l2[q] = (q < pb && two) ? pan[(i2 + q * nf) * TS] : 0.0;
-            }
-            // l[q] is zero beyond the block, so the full-width loop is exact whenever its reads stay inside the front
-            // (always for full blocks); the ragged last block takes the predicated form
-            if (pb == B) {
-                for (int j = pe + ec; j <= nf; j += TC) {
-                    const double* uj;
-                    if constexpr (GLOBAL_F) uj = Ul + j * B * TS;
-                    else uj = Fl + (p0 + j * nf) * TS;
-                    double acc = rowi[j * colstride], acc2 = rowi2[j * colstride];
-#pragma unroll
-                    for (int q = 0; q < B; ++q) {
-                        const double uq = uj[q * TS];
-                        acc -= l[q] * uq;
-                        acc2 -= l2[q] * uq;
-                    }
-                    rowi[j * colstride] = acc;
-                    if (two) rowi2[j * colstride] = acc2;
-                }
-            } else {
-                for (int j = pe + ec; j <= nf; j += TC) {
-                    const double* uj;
-                    if constexpr (GLOBAL_F) uj = Ul + j * B * TS;
-                    else uj = Fl + (p0 + j * nf) * TS;
-                    double acc = rowi[j * colstride], acc2 = rowi2[j * colstride];
-#pragma unroll
-                    for (int q = 0; q < B; ++q) {
-                        if (q < pb) {
-                            const double uq = uj[q * TS];
-                            acc -= l[q] * uq;
-                            acc2 -= l2[q] * uq;
-                        }
-                    }
-                    rowi[j * colstride] = acc;
-                    if (two) rowi2[j * colstride] = acc2;
-                }
-            }
+        // two rows per lane (i and i + TR) share every pivot-row read, two columns per step give four independent
+        // accumulation chains; the panel width is a compile-time constant of the instantiation (most fronts here have 4-12
+        // pivots, so the ragged last panel is the common case and must not pay for eight predicated steps)
+        switch (pb) {
+            case 1: trailing_update<TS, 1, GLOBAL_F>(Fl, pan, Ul, nf, p0, pe, er, ec, TR, TC); break;
+            case 2: trailing_update<TS, 2, GLOBAL_F>(Fl, pan, Ul, nf, p0, pe, er, ec, TR, TC); break;
+            case 3: trailing_update<TS, 3, GLOBAL_F>(Fl, pan, Ul, nf, p0, pe, er, ec, TR, TC); break;
+            case 4: trailing_update<TS, 4, GLOBAL_F>(Fl, pan, Ul, nf, p0, pe, er, ec, TR, TC); break;
+            case 5: trailing_update<TS, 5, GLOBAL_F>(Fl, pan, Ul, nf, p0, pe, er, ec, TR, TC); break;
+            case 6: trailing_update<TS, 6, GLOBAL_F>(Fl, pan, Ul, nf, p0, pe, er, ec, TR, TC); break;
+            case 7: trailing_update<TS, 7, GLOBAL_F>(Fl, pan, Ul, nf, p0, pe, er, ec, TR, TC); break;
+            default: trailing_update<TS, 8, GLOBAL_F>(Fl, pan, Ul, nf, p0, pe, er, ec, TR, TC); break;
         }
         __syncthreads();
     }
@@ -474,6 +497,52 @@ constexpr int kMaxSymFront = 208;
 
 __device__ __forceinline__ int sym_col(int j, int nf) { return (j * (2 * nf - j + 1)) >> 1; }
 
+// Trailing update of the packed lower triangle for one panel of PB pivots (see mf_factor_sym_kernel)
+template <int TS, int PB>
+__device__ __forceinline__ void sym_trailing_update(double* Fl, const double* Lp, double* Rl, int nf, int p0, int pe, int er,
+                                                    int ec, int TR, int TC) {
+    const double* cb[PB];
+#pragma unroll
+    for (int q = 0; q < PB; ++q) cb[q] = Fl + (sym_col(p0 + q, nf) - (p0 + q)) * TS;
+    const int nt = nf - pe;                 // trailing rows pe .. nf-1
+    for (int t = er; 2 * t < nt; t += TR) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            const int i = half == 0 ? pe + t : nf - 1 - t;
+            if (half == 1 && i == pe + t) break;
+            double l[PB];
+#pragma unroll
+            for (int q = 0; q < PB; ++q) l[q] = Lp[(i + q * nf) * TS];
+            int j = pe + ec;
+            for (; j + TC <= i; j += 2 * TC) {          // two columns per step: two independent accumulation chains
+                double* da = Fl + (sym_col(j, nf) + i - j) * TS;
+                double* db = Fl + (sym_col(j + TC, nf) + i - j - TC) * TS;
+                double a = *da, b = *db;
+#pragma unroll
+                for (int q = 0; q < PB; ++q) {
+                    a -= l[q] * cb[q][j * TS];
+                    b -= l[q] * cb[q][(j + TC) * TS];
+                }
+                *da = a;
+                *db = b;
+            }
+            if (j <= i) {
+                double* da = Fl + (sym_col(j, nf) + i - j) * TS;
+                double a = *da;
+#pragma unroll
+                for (int q = 0; q < PB; ++q) a -= l[q] * cb[q][j * TS];
+                *da = a;
+            }
+            if (ec == 0) {
+                double acc = Rl[i * TS];
+#pragma unroll
+                for (int q = 0; q < PB; ++q) acc -= l[q] * Rl[(p0 + q) * TS];
+                Rl[i * TS] = acc;
+            }
+        }
+    }
+}
+
 template <int TS>
 __global__ void __launch_bounds__(TS == 1 ? 1024 : 256)
 mf_factor_sym_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const double* __restrict__ aval,
@@ -548,34 +617,17 @@ mf_factor_sym_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doubl
         }
         __syncthreads();
         // trailing update of the lower triangle, rows folded in pairs (t-th from the top with t-th from the bottom)
-        // so that every lane sweeps the same number of columns
-        const double* cb[B];
-#pragma unroll
-        for (int q = 0; q < B; ++q) cb[q] = Fl + (sym_col(p0 + (q < pb ? q : 0), nf) - (p0 + (q < pb ? q : 0))) * TS;
-        const int nt = nf - pe;                 // trailing rows pe .. nf-1
-        for (int t = er; 2 * t < nt; t += TR) {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int i = half == 0 ? pe + t : nf - 1 - t;
-                if (half == 1 && i == pe + t) break;
-                double l[B];
-#pragma unroll
-                for (int q = 0; q < B; ++q) l[q] = (q < pb) ? Lp[(i + q * nf) * TS] : 0.0;
-                for (int j = pe + ec; j <= i; j += TC) {
-                    double* dstp = Fl + (sym_col(j, nf) + i - j) * TS;
-                    double acc = *dstp;
-#pragma unroll
-                    for (int q = 0; q < B; ++q) acc -= l[q] * cb[q][j * TS];   // l[q] = 0 beyond the block
-                    *dstp = acc;
-                }
-                if (ec == 0) {
-                    double acc = Rl[i * TS];
-#pragma unroll
-                    for (int q = 0; q < B; ++q)
-                        if (q < pb) acc -= l[q] * Rl[(p0 + q) * TS];
-                    Rl[i * TS] = acc;
-                }
-            }
+        // so that every lane sweeps the same number of columns; panel width as a compile-time constant (ragged last
+        // panels are the common case: most fronts have fewer than 16 pivots)
+        switch (pb) {
+            case 1: sym_trailing_update<TS, 1>(Fl, Lp, Rl, nf, p0, pe, er, ec, TR, TC); break;
+            case 2: sym_trailing_update<TS, 2>(Fl, Lp, Rl, nf, p0, pe, er, ec, TR, TC); break;
+            case 3: sym_trailing_update<TS, 3>(Fl, Lp, Rl, nf, p0, pe, er, ec, TR, TC); break;
+            case 4: sym_trailing_update<TS, 4>(Fl, Lp, Rl, nf, p0, pe, er, ec, TR, TC); break;
+            case 5: sym_trailing_update<TS, 5>(Fl, Lp, Rl, nf, p0, pe, er, ec, TR, TC); break;
+            case 6: sym_trailing_update<TS, 6>(Fl, Lp, Rl, nf, p0, pe, er, ec, TR, TC); break;
+            case 7: sym_trailing_update<TS, 7>(Fl, Lp, Rl, nf, p0, pe, er, ec, TR, TC); break;
+            default: sym_trailing_update<TS, 8>(Fl, Lp, Rl, nf, p0, pe, er, ec, TR, TC); break;
         }
         __syncthreads();
     }
