@@ -70,57 +70,64 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 // Trailing update A22 -= L21 U12 of one panel of PB pivots (see mf_factor_kernel): lane (er, ec) owns rows er, er + TR, ...
 // in pairs and every TC-th column; the PB multipliers of its two rows stay in registers, the pivot-row entries are
 // shared-memory broadcasts.
+template <int TS, int PB, bool GLOBAL_F, bool TWO>
+__device__ __forceinline__ void trailing_rows(double* rowi, double* rowi2, const double* l, const double* l2, double* Fl,
+                                              const double* Ul, int nf, int p0, int pe, int ec, int TC) {
+    constexpr int B = 8;
+    const int colstride = nf * TS;
+    int j = pe + ec;
+    for (; j + TC <= nf; j += 2 * TC) {
+        const double *ua, *ub;
+        if constexpr (GLOBAL_F) { ua = Ul + j * B * TS; ub = Ul + (j + TC) * B * TS; }
+        else { ua = Fl + (p0 + j * nf) * TS; ub = Fl + (p0 + (j + TC) * nf) * TS; }
+        double a1 = rowi[j * colstride], b1 = rowi[(j + TC) * colstride], a2 = 0.0, b2 = 0.0;
+        if constexpr (TWO) { a2 = rowi2[j * colstride]; b2 = rowi2[(j + TC) * colstride]; }
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+            const double x = ua[q * TS], y = ub[q * TS];
+            a1 -= l[q] * x;
+            b1 -= l[q] * y;
+            if constexpr (TWO) { a2 -= l2[q] * x; b2 -= l2[q] * y; }
+        }
+        rowi[j * colstride] = a1;
+        rowi[(j + TC) * colstride] = b1;
+        if constexpr (TWO) {
+            rowi2[j * colstride] = a2;
+            rowi2[(j + TC) * colstride] = b2;
+        }
+    }
+    if (j <= nf) {
+        const double* ua;
+        if constexpr (GLOBAL_F) ua = Ul + j * B * TS;
+        else ua = Fl + (p0 + j * nf) * TS;
+        double a1 = rowi[j * colstride], a2 = 0.0;
+        if constexpr (TWO) a2 = rowi2[j * colstride];
+#pragma unroll
+        for (int q = 0; q < PB; ++q) {
+            const double x = ua[q * TS];
+            a1 -= l[q] * x;
+            if constexpr (TWO) a2 -= l2[q] * x;
+        }
+        rowi[j * colstride] = a1;
+        if constexpr (TWO) rowi2[j * colstride] = a2;
+    }
+}
+
 template <int TS, int PB, bool GLOBAL_F>
 __device__ __forceinline__ void trailing_update(double* Fl, const double* pan, const double* Ul, int nf, int p0, int pe,
                                                 int er, int ec, int TR, int TC) {
-    constexpr int B = 8;
-    const int colstride = nf * TS;
     for (int i = pe + er; i < nf; i += 2 * TR) {
         const int i2 = i + TR;
-        const bool two = i2 < nf;
         double* rowi = Fl + i * TS;
-        double* rowi2 = Fl + (two ? i2 : i) * TS;
         double l[PB], l2[PB];
 #pragma unroll
-        for (int q = 0; q < PB; ++q) {
-            l[q] = pan[(i + q * nf) * TS];
-            l2[q] = two ? pan[(i2 + q * nf) * TS] : 0.0;
-        }
-        int j = pe + ec;
-        for (; j + TC <= nf; j += 2 * TC) {
-            const double *ua, *ub;
-            if constexpr (GLOBAL_F) { ua = Ul + j * B * TS; ub = Ul + (j + TC) * B * TS; }
-            else { ua = Fl + (p0 + j * nf) * TS; ub = Fl + (p0 + (j + TC) * nf) * TS; }
-            double a1 = rowi[j * colstride], a2 = rowi2[j * colstride];
-            double b1 = rowi[(j + TC) * colstride], b2 = rowi2[(j + TC) * colstride];
+        for (int q = 0; q < PB; ++q) l[q] = pan[(i + q * nf) * TS];
+        if (i2 < nf) {          // two rows share every pivot-row read
 #pragma unroll
-            for (int q = 0; q < PB; ++q) {
-                const double x = ua[q * TS], y = ub[q * TS];
-                a1 -= l[q] * x;
-                a2 -= l2[q] * x;
-                b1 -= l[q] * y;
-                b2 -= l2[q] * y;
-            }
-            rowi[j * colstride] = a1;
-            rowi[(j + TC) * colstride] = b1;
-            if (two) {
-                rowi2[j * colstride] = a2;
-                rowi2[(j + TC) * colstride] = b2;
-            }
-        }
-        if (j <= nf) {
-            const double* ua;
-            if constexpr (GLOBAL_F) ua = Ul + j * B * TS;
-            else ua = Fl + (p0 + j * nf) * TS;
-            double a1 = rowi[j * colstride], a2 = rowi2[j * colstride];
-#pragma unroll
-            for (int q = 0; q < PB; ++q) {
-                const double x = ua[q * TS];
-                a1 -= l[q] * x;
-                a2 -= l2[q] * x;
-            }
-            rowi[j * colstride] = a1;
-            if (two) rowi2[j * colstride] = a2;
+            for (int q = 0; q < PB; ++q) l2[q] = pan[(i2 + q * nf) * TS];
+            trailing_rows<TS, PB, GLOBAL_F, true>(rowi, Fl + i2 * TS, l, l2, Fl, Ul, nf, p0, pe, ec, TC);
+        } else {
+            trailing_rows<TS, PB, GLOBAL_F, false>(rowi, rowi, l, l, Fl, Ul, nf, p0, pe, ec, TC);
         }
     }
 }

@@ -1,3 +1,4 @@
 #!/bin/bash
-wls() { echo "== $*"; env "$@" python scripts/time_wls.py 1000 2>&1 | grep -E "single WLS|batch WLS|rror"; }
-wls JGB_X=1
+nr() { echo "== $*"; env "$@" python scripts/time_nr.py 10016 2>&1 | grep -E "batch S|check scen|rror" | sed 's/; status.*//'; }
+nr JGB_X=1
+nr JGB_X=2
