@@ -942,7 +942,7 @@ void launch_factor(int ts, dim3 grid, int threads, size_t smem, cudaStream_t st,
 }
 
 // (lanes per scenario, register bound on the front order) variants of the bulk kernel
-#define JGB_BULK_VARIANTS(X) X(4, 8) X(8, 8) X(4, 12) X(8, 12) X(8, 16) X(16, 16)
+#define JGB_BULK_VARIANTS(X) X(4, 6) X(4, 8) X(8, 8) X(4, 10) X(8, 10) X(4, 12) X(8, 12) X(8, 16) X(16, 16)
 
 void launch_factor_bulk(int maxnf, int te, dim3 grid, size_t smem, cudaStream_t st, DevSym dev, const FrontDesc* fronts,
                         const double* aval, const double* rhs, double* U, double* upd, int S, int smem_elems,
@@ -963,6 +963,9 @@ int bulk_variant_for(int nf) {
     // and was 7 % slower on the factor phase than the blocked kernel with 16-scenario tiles
     static const int bulk_max = getenv("JGB_BULK_MAX") ? atoi(getenv("JGB_BULK_MAX")) : 16;
     if (nf > bulk_max || nf > 16) return 0;
+    // JGB_BULK_FINE=0: three register variants (8 / 12 / 16) instead of five (6 / 8 / 10 / 12 / 16)
+    static const bool fine = !(getenv("JGB_BULK_FINE") && atoi(getenv("JGB_BULK_FINE")) == 0);
+    if (fine) return nf <= 6 ? 6 : nf <= 8 ? 8 : nf <= 10 ? 10 : nf <= 12 ? 12 : 16;
     return nf <= 8 ? 8 : nf <= 12 ? 12 : 16;
 }
 // warps per CTA of the small-front kernel by register variant; JGB_BULK_LANES="a,b,c" overrides (tuning only)
@@ -1434,7 +1437,9 @@ void MfSolver::plan(int S) {
     // tree, so wider CTAs pay: measured on the 10k-bus gain matrix 4.21 ms per factorisation with 256 threads, 2.74 ms
     // with 512 threads up to 64 rows and 1024 above (the LU kernel of the Jacobian, fronts <= 66, is best at 256)
     static const std::vector<PlanRule> single_rules_sym = {{64, 1, 512}, {kMaxSymFront, 1, 1024}};
-    static const std::vector<PlanRule> batch_rules = {{8, 32, 128}, {12, 32, 128}, {16, 32, 256}, {20, 16, 256},
+    // small fronts in five register variants (6 / 8 / 10 / 12 / 16 rows: loops are unrolled to the variant's bound, so a
+    // 5-row front in an 8-row variant pays for three idle rows; factor phase 36.1 -> 35.2 ms against three variants)
+    static const std::vector<PlanRule> batch_rules = {{6, 32, 128}, {8, 32, 128}, {10, 32, 128}, {12, 32, 128}, {16, 32, 256}, {20, 16, 256},
                                                       {24, 8, 256}, {32, 8, 256}, {48, 4, 256}, {64, 2, 256},
                                                       {96, 1, 256}, {kMaxSmemFront, 1, 256},
                                                       {kMaxSymFront, 1, 256}};
