@@ -1618,6 +1618,19 @@ void MfSolver::plan(int S) {
                 // (measured 1.77 -> 1.38 ms per gain factorisation, 358 -> 428 GN iterations/s; JGB_DENSE_THREADS overrides)
                 if (S == 1) fl.threads = dense_threads_single > 0 ? std::min(512, dense_threads_single) : 512;
                 fl.smem = dense_smem_doubles(nf) * sizeof(double);
+                if (S > 1) {
+                    // batches: when shared memory leaves room for one or two CTAs per SM only, wider CTAs keep the SM's warp
+                    // slots busy (JGB_DENSE_WIDE="t1,t2": threads at one / two CTAs per SM; tuning only)
+                    static int wide1 = 512, wide2 = 384;      // measured per 1000 draws: 256,256 25.43 ms; 512,256 25.07; 512,384 24.49; 512,512 25.94
+                    static bool init = false;
+                    if (!init) {
+                        init = true;
+                        if (const char* e = getenv("JGB_DENSE_WIDE")) sscanf(e, "%d,%d", &wide1, &wide2);
+                    }
+                    const size_t ctas = 233472 / (fl.smem + 1024);
+                    if (ctas <= 1) fl.threads = wide1;
+                    else if (ctas == 2) fl.threads = wide2;
+                }
                 fl.tr = 1;
                 fl.gstride = 0;
                 fplan.push_back(fl);
@@ -1775,9 +1788,16 @@ void MfSolver::plan(int S) {
                 sl.max_nf = std::max(sl.max_nf, nf);
                 sl.max_k = std::max(sl.max_k, k);
             }
+            int tile_ts = 0;
             if (S > 1 && full <= 200 * 1024) {
-                sl.ts = std::min(brules[c].ts, S);
-                while (sl.ts > 1 && full * sl.ts > 100 * 1024) sl.ts /= 2;
+                tile_ts = std::min(brules[c].ts, S);
+                while (tile_ts > 1 && full * tile_ts > 100 * 1024) tile_ts /= 2;
+            }
+            // single-scenario tiles (the big fronts at the top of the tree) take the blocked kernel: a warp per pivot row
+            // with a shuffle reduction instead of one lane per row (JGB_BS_TS1_TILE=1 keeps the tile kernel; tuning only)
+            static const bool ts1_tile = getenv("JGB_BS_TS1_TILE") && atoi(getenv("JGB_BS_TS1_TILE")) == 1;
+            if (tile_ts >= 2 || (tile_ts == 1 && ts1_tile)) {
+                sl.ts = tile_ts;
                 smem = full * sl.ts;
             } else {
                 // single case, or a batch front whose packed rows do not fit shared memory: blocks of 32 rows

@@ -1,8 +1,6 @@
 #!/bin/bash
-nr() { echo "== $*"; env "$@" python scripts/time_nr.py 10016 2>&1 | grep -E "batch S|rror" | sed 's/; status.*//'; }
-P="6:32:128,8:32:128,10:32:128,12:32:128,16:32:256"
-T="96:1:256,150:1:256,208:1:256"
-nr JGB_FPLAN_BATCH="$P,20:16:256,24:8:256,32:8:256,40:8:256,48:4:256,64:2:256,$T"
-nr JGB_FPLAN_BATCH="$P,20:16:256,24:8:256,36:8:256,48:4:256,64:2:256,$T"
-nr JGB_FPLAN_BATCH="$P,20:16:256,28:8:256,36:4:256,48:4:256,64:2:256,$T"
-nr JGB_FPLAN_BATCH="$P,18:16:256,22:16:256,24:8:256,32:8:256,48:4:256,64:2:256,$T"
+wls() { echo "== $*"; env "$@" python scripts/time_wls.py 1000 2>&1 | grep -E "batch WLS|rror"; }
+wls JGB_BS_TS1_TILE=1
+wls JGB_BS_TS1_TILE=0
+wls JGB_BS_TS1_TILE=0 JGB_BS_THREADS=256
+wls JGB_BS_TS1_TILE=0 JGB_BS_THREADS=128
