@@ -573,6 +573,19 @@ def nr_leg(job, S, extras=True, strong_total=None):
                                             "launches (one CTA per front), not by HBM"}
         single["nr_single_case"]["hbm_frac"] = (single["nr_single_case"]["bytes_per_iteration_8d"]
                                                 / (single["nr_single_case"]["ms_per_iteration"] * 1e-3) / 1e9 / hbm)
+        # where the iteration goes: CUDA-event phase times of one more (untimed) solve; the rest is the assembly / update /
+        # convergence kernels, the per-iteration 16-byte read-back and launch gaps
+        lib.jgb_profile(ctx.handle, 1)
+        jgb200.set_initial_point(a)
+        a._push_state()
+        jgb200.power_flow(a)
+        nfc = max(1.0, ctx.stat("nr.time.factor_count"))
+        fac_us, bs_us = 1e3 * ctx.stat("nr.time.factor_ms") / nfc, 1e3 * ctx.stat("nr.time.backsolve_ms") / nfc
+        lib.jgb_profile(ctx.handle, 0)
+        single["nr_single_case"]["per_iteration_us"] = {
+            "factor_levels": fac_us, "backsolve_levels": bs_us,
+            "assembly_update_check_readback_gaps": 1e3 * single["nr_single_case"]["ms_per_iteration"] - fac_us - bs_us,
+            "launch_list": "profiles/r02_launch_summary_nr_single.txt (21 + 21 level launches, 15-45 us / 7-20 us each)"}
     return result, {"roofline": roofline, "cpu_baseline": cpu, **single}, (ps, base_vm, base_va), a
 
 

@@ -132,6 +132,9 @@ __device__ __forceinline__ void trailing_update(double* Fl, const double* pan, c
     }
 }
 
+#ifndef JGB_MID_MINBLOCKS
+#define JGB_MID_MINBLOCKS 3
+#endif
 constexpr int kEaChunkCache = 96;      // chunk descriptors of a front kept in shared memory (ring-mode extend-add)
 
 // One CTA = one front x TS scenarios. Thread t: scenario lane sl = t % TS, entry lane e = t / TS,
@@ -139,7 +142,7 @@ constexpr int kEaChunkCache = 96;      // chunk descriptors of a front kept in s
 // element (r,c) of scenario lane sl at F[(r + c*nf) * TS + sl].  TS and the address space of F are compile-time
 // so that the front is addressed with LDS/STS and shifts (a runtime select would degrade to generic LD/ST).
 template <int TS, bool GLOBAL_F>
-__global__ void __launch_bounds__(TS == 1 ? 512 : 256, TS == 1 ? 1 : 3)
+__global__ void __launch_bounds__(TS == 1 ? 512 : 256, TS == 1 ? 1 : JGB_MID_MINBLOCKS)
 mf_factor_kernel(DevSym sy, const int* __restrict__ fronts, const FrontDesc* __restrict__ descs,
                  const double* __restrict__ aval, const double* __restrict__ rhs, double* __restrict__ U,
                  double* __restrict__ upd, int S, int TR, const unsigned char* __restrict__ active,
@@ -1713,7 +1716,7 @@ void MfSolver::plan(int S) {
             if (staged_enabled && !fl.sym && !fl.bulk && !fl.global_front && fl.ts >= 2 && S % fl.ts == 0) {
                 // ring of two stages behind the largest front of the launch: the largest stage (8 KB .. 1 KB) that keeps
                 // the number of resident CTAs the front alone allows (at most 3: registers)
-                auto ctas = [](size_t bytes) { return std::min<size_t>(3, 233472 / (bytes + 1024)); };
+                auto ctas = [](size_t bytes) { return std::min<size_t>(JGB_MID_MINBLOCKS, 233472 / (bytes + 1024)); };
                 size_t stage = 8192;
                 while (stage > 1024 && (ctas(fl.smem + 2 * stage) < ctas(fl.smem) || fl.smem + 2 * stage > 200 * 1024)) stage /= 2;
                 if (fl.smem + 2 * stage <= 200 * 1024 && ctas(fl.smem + 2 * stage) == ctas(fl.smem)) {

@@ -1,6 +1,4 @@
 #!/bin/bash
-wls() { echo "== $*"; env "$@" python scripts/time_wls.py 1000 2>&1 | grep -E "batch WLS|rror"; }
-wls JGB_BS_TS1_TILE=1
-wls JGB_BS_TS1_TILE=0
-wls JGB_BS_TS1_TILE=0 JGB_BS_THREADS=256
-wls JGB_BS_TS1_TILE=0 JGB_BS_THREADS=128
+nr() { echo "== $*"; env "$@" python scripts/time_nr.py 10016 2>&1 | grep -E "batch S|check scen|rror" | sed 's/; status.*//'; }
+nr JGB_X=1
+nr JGB200_LIB=$PWD/build/alt/libjgb200_mb4.so
