@@ -584,7 +584,9 @@ def nr_leg(job, S, extras=True, strong_total=None):
         lib.jgb_profile(ctx.handle, 0)
         single["nr_single_case"]["per_iteration_us"] = {
             "factor_levels": fac_us, "backsolve_levels": bs_us,
-            "assembly_update_check_readback_gaps": 1e3 * single["nr_single_case"]["ms_per_iteration"] - fac_us - bs_us,
+            "note": "CUDA-event spans of a separate run with the phase timers on (launches issued one by one instead of "
+                    "the replayed graph, so the two spans include their launch gaps); what is left of ms_per_iteration is "
+                    "assembly + update + convergence test + the 16-byte read-back",
             "launch_list": "profiles/r02_launch_summary_nr_single.txt (21 + 21 level launches, 15-45 us / 7-20 us each)"}
     return result, {"roofline": roofline, "cpu_baseline": cpu, **single}, (ps, base_vm, base_va), a
 
