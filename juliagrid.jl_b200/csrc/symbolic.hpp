@@ -40,8 +40,10 @@ inline SymbolicOptions latency_options() {
 }
 inline SymbolicOptions throughput_options() {
     SymbolicOptions o;
-    o.relax_small = 4; o.relax_mid = 8; o.relax_mid_frac = 0.3; o.relax_big = 24; o.relax_big_frac = 0.1;
-    o.relax_any_frac = 0.02;
+    // re-tuned against the round-2 kernels (small fronts run at 2-3 TB/s, the scenario-tile kernel at 0.8-1.6: less
+    // amalgamation pays): 4,8,0.3,24,0.1,0.02 -> factor 35.2 / back-solve 6.7 ms per 10 016 scenarios; these 33.8 / 6.4
+    o.relax_small = 2; o.relax_mid = 6; o.relax_mid_frac = 0.2; o.relax_big = 16; o.relax_big_frac = 0.05;
+    o.relax_any_frac = 0.01;
     return o;
 }
 
