@@ -2066,6 +2066,13 @@ void MfSolver::plan(int S) {
             if (!fork_event) JGB_CUDA(cudaEventCreateWithFlags(&fork_event, cudaEventDisableTiming));
         }
     }
+    // scenario tiles sit in gridDim.y: a batch whose smallest tile width needs more than 65 535 tiles cannot be launched
+    for (const FactorLaunch& fl : fplan)
+        if (S / std::max(1, fl.ts) > 65535)
+            throw std::invalid_argument("batch too large for the scenario tiles of this matrix (more than 65 535 tiles): split it");
+    for (const SolveLaunch& sl : splan)
+        if ((sl.blocked ? S : S / std::max(1, sl.ts)) > 65535 && S > 1)
+            throw std::invalid_argument("batch too large for the back-solve tiles of this matrix (more than 65 535 tiles): split it");
     if (getenv("JGB_PLAN_DEBUG")) {
         for (const FactorLaunch& fl : fplan)
             fprintf(stderr, "[plan S=%d] fronts %4d nf<=%3d ts %2d threads %4d smem %6zu %s%s%s%s%s ring %d\n", S, fl.count,
