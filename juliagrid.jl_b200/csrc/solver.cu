@@ -22,18 +22,19 @@ __device__ __forceinline__ size_t wide(int a, int b) { return (size_t)(unsigned)
 // log2 of a power-of-two tile width (1..32)
 __host__ __device__ __forceinline__ int lg2(int w) { return w >= 32 ? 5 : w >= 16 ? 4 : w >= 8 ? 3 : w >= 4 ? 2 : w >= 2 ? 1 : 0; }
 // base of scenario s in the update-storage section of tile width W (see DevSym): add (off + e) * W for an element
+// (W is a power of two: shifts and masks instead of the integer division a runtime W would cost in every thread)
 __device__ __forceinline__ double* upd_base(double* upd, const DevSym& sy, int W, int s) {
     const int lw = lg2(W);
-    return upd + sy.sec_base[lw] + (long long)(s / W) * sy.sec_size[lw] * W + (s % W);
+    return upd + sy.sec_base[lw] + (((long long)(s >> lw) * sy.sec_size[lw]) << lw) + (s & (W - 1));
 }
 // same for the packed U rows (usec_* sections): add (f_uoff + e) * W for an entry
 __device__ __forceinline__ double* u_base(double* U, const DevSym& sy, int W, int s) {
     const int lw = lg2(W);
-    return U + sy.usec_base[lw] + (long long)(s / W) * sy.usec_size[lw] * W + (s % W);
+    return U + sy.usec_base[lw] + (((long long)(s >> lw) * sy.usec_size[lw]) << lw) + (s & (W - 1));
 }
 __device__ __forceinline__ const double* u_base(const double* U, const DevSym& sy, int W, int s) {
     const int lw = lg2(W);
-    return U + sy.usec_base[lw] + (long long)(s / W) * sy.usec_size[lw] * W + (s % W);
+    return U + sy.usec_base[lw] + (((long long)(s >> lw) * sy.usec_size[lw]) << lw) + (s & (W - 1));
 }
 __device__ __forceinline__ unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
 
@@ -764,7 +765,10 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
     }
     if (ring_mode)
         for (int c = threadIdx.x; c < nch && c < kEaChunkCache; c += blockDim.x) ea_ch[c] = sg.chunks[c0 + c];
-    for (int pos = e0; pos < fsz; pos += TE) Fl[pos * 32] = 0.0;
+    {
+        double2* F2 = reinterpret_cast<double2*>(sm);          // 16-byte stores: half the instructions of the zeroing pass
+        for (int pos = threadIdx.x; pos < fsz * 16; pos += blockDim.x) F2[pos] = make_double2(0.0, 0.0);
+    }
     __syncthreads();
     {
 #pragma unroll
