@@ -765,10 +765,7 @@ mf_factor_bulk_kernel(DevSym sy, const FrontDesc* __restrict__ descs, const doub
     }
     if (ring_mode)
         for (int c = threadIdx.x; c < nch && c < kEaChunkCache; c += blockDim.x) ea_ch[c] = sg.chunks[c0 + c];
-    {
-        double2* F2 = reinterpret_cast<double2*>(sm);          // 16-byte stores: half the instructions of the zeroing pass
-        for (int pos = threadIdx.x; pos < fsz * 16; pos += blockDim.x) F2[pos] = make_double2(0.0, 0.0);
-    }
+    for (int pos = e0; pos < fsz; pos += TE) Fl[pos * 32] = 0.0;
     __syncthreads();
     {
 #pragma unroll
