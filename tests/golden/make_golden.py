@@ -10,6 +10,8 @@ Reads the reference's own test inputs and MATPOWER-generated golden vectors
   tests/golden/case14test.json, case30test.json   parsed inputs (per-unit, 0-based) + golden NR outputs
   tests/golden/case_ACTIVSg10k.npz                parsed 10k-bus case (inputs only)
   tests/golden/known_answers.json                 WLS known answers of test/stateEstimation/badData.jl:24-41
+  tests/golden/monitoring14.json                  the reference's own measurement file src/data/monitoring.h5 (datasets
+                                                  in the saveMeasurement layout) + its power system src/data/case14.h5
 
 /root/reference does not exist on the GPU box, so tests only ever read these fixtures.
 """
@@ -72,6 +74,26 @@ def main(ref="/root/reference"):
     np.savez_compressed(os.path.join(HERE, "case_ACTIVSg70k.npz"), n=s.n, nbr=s.nbr, ngen=s.ngen, slack=s.slack,
                         base_mva=s.base_mva, **{k: getattr(s, k) for k in SYS_FIELDS})
     print("ACTIVSg70k", s.n, s.nbr, s.ngen, os.path.getsize(os.path.join(HERE, "case_ACTIVSg70k.npz")))
+
+    # a measurement file written by the reference's saveMeasurement (src/data/monitoring.h5, the companion of
+    # src/data/case14.h5): the dataset dictionary in the file's own layout + the power system it belongs to
+    mon = H5File(os.path.join(ref, "src/data/monitoring.h5"))
+    datasets = {}
+    for dev in mon.keys("/"):
+        for sub in mon.keys("/" + dev):
+            if not mon.is_group(f"/{dev}/{sub}"):
+                continue                                   # labels are not kept (meters are addressed by position)
+            for k in mon.keys(f"/{dev}/{sub}"):
+                if k == "label":
+                    continue
+                a = np.asarray(mon[f"/{dev}/{sub}/{k}"])
+                datasets[f"{dev}/{sub}/{k}"] = a.reshape(-1).tolist() if a.ndim else a.item()
+    s14 = load_hdf5(os.path.join(ref, "src/data/case14.h5"))
+    out = {"source": "src/data/monitoring.h5 (saveMeasurement layout, measurement/save.jl:40-118) + src/data/case14.h5",
+           "system": system_dict(s14), "attrs": {k: int(v) for k, v in mon.attrs("/").items()}, "datasets": datasets}
+    with open(os.path.join(HERE, "monitoring14.json"), "w") as fh:
+        json.dump(out, fh)
+    print("monitoring14", out["attrs"])
 
     known = {
         "badData_one_outlier": {

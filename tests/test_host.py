@@ -404,3 +404,46 @@ def test_measurement_file_layout_round_trip():
     bad["voltmeter/layout/index"] = data["voltmeter/layout/index"] + ps.n
     with pytest.raises(ValueError):
         jgb200.measurement_from_arrays(ps, bad)
+
+
+def test_reference_measurement_file():
+    """The reference's own measurement file (src/data/monitoring.h5, written by saveMeasurement for src/data/case14.h5;
+    fixture tests/golden/monitoring14.json): the loader of measurement(system, "file.h5") (load.jl:31-273) rebuilds the
+    five device classes with the counts of the file's attributes, scalar datasets as constant vectors and Bool bitfields as
+    flags; the acWLS tables of the product and of the oracle agree on it, and the oracle's Gauss-Newton estimation of this
+    real measurement set converges. Where the reference tree is present the HDF5 file itself is read and compared."""
+    import json
+    path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "monitoring14.json")
+    with open(path) as fh:
+        g = json.load(fh)
+    ps = jgb200.power_system(path)
+    ps.model = jgb200.ac_model(ps)
+    data = {k: np.asarray(v) for k, v in g["datasets"].items()}
+    mon = jgb200.measurement_from_arrays(ps, data)
+    at = g["attrs"]
+    assert len(mon.volt["index"]) == at["number of voltmeters"] == 14
+    assert len(mon.amp["index"]) == at["number of ammeters"] == 2 * len(ps.status)
+    assert len(mon.watt["index"]) == at["number of wattmeters"] == ps.n + 2 * len(ps.status)
+    assert len(mon.var["index"]) == at["number of varmeters"] and len(mon.pmu["index"]) == at["number of pmus"]
+    assert mon.volt["variance"].shape == (14,) and np.all(mon.volt["variance"] == 1e-4)      # scalar dataset
+    assert mon.amp["frm"].dtype == bool and mon.amp["frm"][:4].tolist() == [True, False, True, False]
+    assert mon.amp["square"].all() and not mon.pmu["polar"].any()
+    assert mon.watt["bus"][:ps.n].all() and not mon.watt["bus"][ps.n:].any()
+    ref_file = "/root/reference/src/data/monitoring.h5"
+    if os.path.exists(ref_file):
+        mon2 = jgb200.load_measurement(ps, ref_file)
+        for dev in ("volt", "amp", "watt", "var", "pmu"):
+            for k, v in getattr(mon, dev).items():
+                assert np.array_equal(getattr(mon2, dev)[k], v), (dev, k)
+    # the same tables on both sides, and a converging estimation on the CPU oracle
+    os_ = oracle.system_from_arrays(g["system"])
+    mdl = oracle.ac_model(os_)
+    t = jgb200.ac_wls(ps, mon)
+    gn = owls.gauss_newton(os_, mon, mdl)
+    ex = owls.export_one_based(gn)
+    assert t.m == gn.m == 14 + 40 + 54 + 54 + 2 * 54
+    for k in ("h_colptr", "h_rowval", "type", "index", "range"):
+        assert np.array_equal(getattr(t, k), ex[k]), k
+    assert np.array_equal(t.mean, gn.mean)
+    assert owls.state_estimation(gn, iteration=40, tolerance=1e-8)
+    assert np.abs(gn.vm - mon.volt["mean"]).max() < 0.05          # the estimate sits on the (noisy) voltmeter readings
