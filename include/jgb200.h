@@ -71,7 +71,11 @@ int32_t jgb_nr_run(jgb_ctx* ctx, int64_t max_iter, double tol, int64_t* iteratio
  * nodalToFrom / nodalToTo are given in dy_re_im[s][0..7].  Every scenario starts from the state that is on the
  * device when the call is made: the one last set with jgb_nr_set_state, or the iterate a later jgb_nr_solve /
  * jgb_nr_run left there (call jgb_nr_set_state with the start point first for setInitialPoint! semantics).  Outputs are S x n row-major (one row per scenario); status[s] is
- * 0 converged, 1 iteration cap, -3 singular (islanding outage).  *total_iterations = sum of solve! calls. */
+ * 0 converged, 1 iteration cap, -3 singular (islanding outage).  *total_iterations = sum of solve! calls.
+ * Batch size: scenario tiles sit in gridDim.y, so a call takes at most 65 535 tiles of the narrowest tile width the
+ * matrix needs (32 scenarios per tile for fronts up to 16 rows ... 1 above 64 rows): S <= 65 535 always works, larger S
+ * only for matrices without large fronts; otherwise the call returns -1 and the caller splits the batch (the same holds
+ * for jgb_wls_batch). */
 int32_t jgb_nr_batch(jgb_ctx* ctx, int64_t S, const int64_t* out_from, const int64_t* out_to, const double* dy_re_im,
                      int64_t max_iter, double tol, double* vm_out, double* va_out, int32_t* iterations,
                      int8_t* status, int64_t* total_iterations);
